@@ -1,0 +1,421 @@
+// api.cu -- C ABI of libgptpinn_b200.so (include/gptpinn_b200.h): argument checking, grouping of
+// the parameter grid into warp work items, packing, launch.  No CPU fallback: a device that is
+// not sm_100 is rejected with GPTPINN_E_UNSUPPORTED.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/gptpinn_b200.h"
+#include "pack.cuh"
+#include "precomp.cuh"
+#include "sweep_kernel.cuh"
+
+namespace gp {
+#define GP_DECL(P, N) cudaError_t sweep_launch_##P##_##N(const SweepParams &, int, int, size_t, cudaStream_t);
+#define GP_DECL_ALL(P) GP_DECL(P, 1) GP_DECL(P, 2) GP_DECL(P, 3) GP_DECL(P, 4) GP_DECL(P, 5) GP_DECL(P, 6) GP_DECL(P, 7) GP_DECL(P, 8) GP_DECL(P, 9)
+GP_DECL_ALL(0) GP_DECL_ALL(1) GP_DECL_ALL(2)
+GP_DECL(0, 10) GP_DECL(0, 11) GP_DECL(0, 12) GP_DECL(0, 13) GP_DECL(0, 14) GP_DECL(0, 15)
+#define GP_ROW9(P) sweep_launch_##P##_1, sweep_launch_##P##_2, sweep_launch_##P##_3, sweep_launch_##P##_4, sweep_launch_##P##_5, sweep_launch_##P##_6, sweep_launch_##P##_7, sweep_launch_##P##_8, sweep_launch_##P##_9
+static const sweep_launch_fn kLaunch[3][15] = {
+    {GP_ROW9(0), sweep_launch_0_10, sweep_launch_0_11, sweep_launch_0_12, sweep_launch_0_13, sweep_launch_0_14, sweep_launch_0_15},
+    {GP_ROW9(1), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr},
+    {GP_ROW9(2), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}};
+static const int kMaxN[3] = {15, 9, 9};
+}  // namespace gp
+
+using namespace gp;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(x)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e__ = (x);                                                                        \
+        if (e__ != cudaSuccess) return fail(GPTPINN_E_CUDA, "%s failed: %s", #x, cudaGetErrorString(e__)); \
+    } while (0)
+
+struct gptpinn_handle {
+    int device = -1;
+    int n_sm = 0;
+    float *packed = nullptr;   size_t packed_cap = 0;     // floats
+    void *items = nullptr;     size_t items_cap = 0;      // bytes
+    void *sibs = nullptr;      size_t sibs_cap = 0;       // bytes
+};
+
+static int ensure(void **ptr, size_t *cap, size_t need)
+{
+    if (need <= *cap) return GPTPINN_OK;
+    if (*ptr) { cudaError_t e = cudaFree(*ptr); *ptr = nullptr; *cap = 0; if (e != cudaSuccess) return fail(GPTPINN_E_CUDA, "cudaFree: %s", cudaGetErrorString(e)); }
+    size_t want = need + need / 4 + 4096;
+    cudaError_t e = cudaMalloc(ptr, want);
+    if (e != cudaSuccess) return fail(GPTPINN_E_NOMEM, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+    *cap = want;
+    return GPTPINN_OK;
+}
+
+extern "C" int gptpinn_version(void) { return 100; }
+extern "C" const char *gptpinn_last_error(void) { return g_err; }
+
+extern "C" int gptpinn_create(gptpinn_handle **out)
+{
+    if (!out) return fail(GPTPINN_E_INVALID, "gptpinn_create: out is NULL");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        return fail(GPTPINN_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only (no fallback)",
+                    dev, prop.major, prop.minor);
+    gptpinn_handle *h = new (std::nothrow) gptpinn_handle();
+    if (!h) return fail(GPTPINN_E_NOMEM, "out of host memory");
+    h->device = dev;
+    h->n_sm = prop.multiProcessorCount;
+    *out = h;
+    return GPTPINN_OK;
+}
+
+extern "C" int gptpinn_destroy(gptpinn_handle *h)
+{
+    if (!h) return GPTPINN_OK;
+    if (h->packed) cudaFree(h->packed);
+    if (h->items) cudaFree(h->items);
+    if (h->sibs) cudaFree(h->sibs);
+    delete h;
+    return GPTPINN_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// grid -> work items
+// ------------------------------------------------------------------------------------------
+struct ParamRow { float tp0, tp1, sp0, sp1; int idx; };
+
+static inline uint64_t key_of(const ParamRow &r)
+{
+    uint32_t a, b;
+    memcpy(&a, &r.tp0, 4);
+    memcpy(&b, &r.tp1, 4);
+    return ((uint64_t)a << 32) | b;
+}
+
+struct Plan {
+    int M = 1, SL = 1, W = 1, ctas = 1, rounds = 1, groups = 0;
+    std::vector<ItemDesc> items;
+    std::vector<SibDesc> sibs;
+};
+
+static double model_cost(int n, int M, int SL, int W, long long items, int n_sm, int rounds, long long rows)
+{
+    const int RL = 32 / SL;
+    const double rows_lane = (double)rows / RL;
+    const double per_row = M * (4.0 * n + 8.0) + 2.0 * ((n + 3) / 4) + 6.0;
+    const double build = (double)rows / R_TILE * 25.0 * (n / 4 + 1) * R_TILE / 32.0;
+    const double issue = std::ceil(W / 4.0) * (rows_lane * per_row + build);
+    const double wf = std::max(1.0, RL / 8.0);
+    const double smem = (double)W * rows_lane * 2.0 * ((n + 3) / 4) * wf;
+    (void)items; (void)n_sm;
+    return rounds * std::max(issue, smem);
+}
+
+static int make_plan(std::vector<ParamRow> &rows, int n, int n_sm, long long data_rows,
+                     const gptpinn_sweep_args *a, Plan &plan)
+{
+    std::stable_sort(rows.begin(), rows.end(), [](const ParamRow &x, const ParamRow &y) { return key_of(x) < key_of(y); });
+    std::vector<int> gstart;
+    for (size_t i = 0; i < rows.size(); ++i)
+        if (i == 0 || key_of(rows[i]) != key_of(rows[i - 1])) gstart.push_back((int)i);
+    gstart.push_back((int)rows.size());
+    plan.groups = (int)gstart.size() - 1;
+
+    auto count_items = [&](int M, int SL) {
+        long long it = 0;
+        for (int g = 0; g < plan.groups; ++g) { int S = gstart[g + 1] - gstart[g]; it += (S + M * SL - 1) / (M * SL); }
+        return it;
+    };
+    static const int Ms[4] = {5, 4, 2, 1};
+    int bestM = 0, bestSL = 0, bestW = 0;
+    if (a->cfg_M > 0 && a->cfg_SL > 0) {
+        bestM = a->cfg_M; bestSL = a->cfg_SL;
+        if (!(bestM == 1 || bestM == 2 || bestM == 4 || bestM == 5)) return fail(GPTPINN_E_INVALID, "cfg_M must be 1, 2, 4 or 5");
+        if (bestSL < 1 || bestSL > 32 || (bestSL & (bestSL - 1))) return fail(GPTPINN_E_INVALID, "cfg_SL must be a power of two <= 32");
+        long long it = count_items(bestM, bestSL);
+        int maxw = maxw_for_m(bestM);
+        bestW = a->cfg_W > 0 ? std::min(a->cfg_W, maxw) : (int)std::min<long long>(maxw, (it + n_sm - 1) / n_sm);
+    } else {
+        double best = 1e300;
+        for (int mi = 0; mi < 4; ++mi)
+            for (int SL = 1; SL <= 32; SL <<= 1) {
+                const int M = Ms[mi];
+                const long long it = count_items(M, SL);
+                const int maxw = maxw_for_m(M);
+                for (int W = 1; W <= maxw; ++W) {
+                    if (a->cfg_W > 0 && W != std::min(a->cfg_W, maxw)) continue;
+                    const long long ctas = std::min<long long>(n_sm, (it + W - 1) / W);
+                    const int rounds = (int)((it + ctas * W - 1) / (ctas * W));
+                    const double cst = model_cost(n, M, SL, W, it, n_sm, rounds, data_rows);
+                    if (cst < best) { best = cst; bestM = M; bestSL = SL; bestW = W; }
+                }
+            }
+    }
+    plan.M = bestM; plan.SL = bestSL; plan.W = std::max(1, bestW);
+    const int cap = plan.M * plan.SL;
+    plan.items.clear(); plan.sibs.clear();
+    plan.sibs.reserve(rows.size());
+    for (int g = 0; g < plan.groups; ++g) {
+        for (int s0 = gstart[g]; s0 < gstart[g + 1]; s0 += cap) {
+            ItemDesc it;
+            memset(&it, 0, sizeof(it));
+            it.tp0 = rows[s0].tp0; it.tp1 = rows[s0].tp1;
+            it.sib_start = (int)plan.sibs.size();
+            it.sib_count = std::min(cap, gstart[g + 1] - s0);
+            it.SL = plan.SL;
+            for (int s = 0; s < it.sib_count; ++s) {
+                SibDesc sd;
+                sd.sp0 = rows[s0 + s].sp0; sd.sp1 = rows[s0 + s].sp1; sd.out_idx = rows[s0 + s].idx; sd.pad = 0;
+                plan.sibs.push_back(sd);
+            }
+            plan.items.push_back(it);
+        }
+    }
+    const long long nit = (long long)plan.items.size();
+    plan.ctas = (int)std::min<long long>(n_sm, (nit + plan.W - 1) / plan.W);
+    plan.rounds = (int)((nit + (long long)plan.ctas * plan.W - 1) / ((long long)plan.ctas * plan.W));
+    return GPTPINN_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// common driver
+// ------------------------------------------------------------------------------------------
+struct Segments { long long rows[MAX_SEG]; int nseg; };
+
+static int run_sweep(gptpinn_handle *h, int pde, int n, const Segments &seg, PackJobs &jobs, bool has_fhat,
+                     int NR, int NI, int NB, std::vector<ParamRow> &rows, const gptpinn_sweep_args *a,
+                     gptpinn_sweep_info *info, cudaStream_t st)
+{
+    int dev = -1;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != h->device) return fail(GPTPINN_E_INVALID, "handle belongs to device %d, current device is %d", h->device, dev);
+    if (a->epochs < 0) return fail(GPTPINN_E_INVALID, "epochs < 0");
+    if (!a->f_out_dev || !a->m_out_dev || !a->c0_dev) return fail(GPTPINN_E_INVALID, "f_out_dev, m_out_dev and c0_dev are required");
+
+    Plan plan;
+    int rc = make_plan(rows, n, h->n_sm, seg.rows[0], a, plan);
+    if (rc) return rc;
+
+    const int slot = pde == PDE_KG ? SlotFloats<PDE_KG>::value : (pde == PDE_B ? SlotFloats<PDE_B>::value : SlotFloats<PDE_AC>::value);
+    SweepParams p;
+    memset(&p, 0, sizeof(p));
+    long long tiles = 0, max_rows = 0;
+    long long tile0[MAX_SEG];
+    for (int s = 0; s < seg.nseg; ++s) {
+        tile0[s] = tiles;
+        p.ntile[s] = (int)((seg.rows[s] + R_TILE - 1) / R_TILE);
+        tiles += p.ntile[s];
+        max_rows = std::max(max_rows, seg.rows[s]);
+    }
+    for (int i = 0; i < jobs.nmat; ++i) jobs.mat[i].tile0 = tile0[jobs.mat[i].tile0];
+    for (int i = 0; i < jobs.nvec; ++i) jobs.vec[i].tile0 = tile0[jobs.vec[i].tile0];
+    jobs.slot = slot;
+    const unsigned long long total_tiles = (unsigned long long)plan.rounds * (unsigned long long)(a->epochs + 1) * (unsigned long long)tiles;
+    if (total_tiles >= 0xfffffff0ull) return fail(GPTPINN_E_UNSUPPORTED, "rounds*epochs*tiles = %llu overflows the tile counter", total_tiles);
+
+    size_t cap_f = h->packed_cap * sizeof(float);
+    rc = ensure((void **)&h->packed, &cap_f, (size_t)tiles * slot * sizeof(float));
+    h->packed_cap = cap_f / sizeof(float);
+    if (rc) return rc;
+    rc = ensure(&h->items, &h->items_cap, plan.items.size() * sizeof(ItemDesc));
+    if (rc) return rc;
+    rc = ensure(&h->sibs, &h->sibs_cap, plan.sibs.size() * sizeof(SibDesc));
+    if (rc) return rc;
+
+    CUDA_TRY(cudaMemsetAsync(h->packed, 0, (size_t)tiles * slot * sizeof(float), st));
+    CUDA_TRY(launch_pack(jobs, h->packed, max_rows, st));
+    CUDA_TRY(cudaMemcpyAsync(h->items, plan.items.data(), plan.items.size() * sizeof(ItemDesc), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->sibs, plan.sibs.data(), plan.sibs.size() * sizeof(SibDesc), cudaMemcpyHostToDevice, st));
+    // pageable sources: the copies above have consumed the host vectors when the calls return
+
+    p.packed = h->packed;
+    p.tiles_per_pass = (int)tiles;
+    p.nR = (float)NR; p.nI = (float)NI; p.nB = (float)NB;
+    p.fac1 = (float)(2.0 / NR); p.fac2 = (float)(2.0 / NB); p.fac3 = (float)(2.0 / NI);
+    p.lr = (float)a->lr;
+    p.epochs = a->epochs;
+    p.rec_every = (a->trace_dev && a->rec_every > 0) ? a->rec_every : 0;
+    p.nrec = p.rec_every > 0 ? a->epochs / p.rec_every + 1 : 0;
+    p.has_fhat = has_fhat ? 1 : 0;
+    p.items = (const ItemDesc *)h->items;
+    p.n_items = (int)plan.items.size();
+    p.sibs = (const SibDesc *)h->sibs;
+    p.c0 = a->c0_dev;
+    p.c0_per_param = a->c0_per_param;
+    p.c_out = a->c_out_dev; p.f_out = a->f_out_dev; p.m_out = a->m_out_dev;
+    p.trace = p.rec_every > 0 ? a->trace_dev : nullptr;
+    p.W = plan.W;
+    p.rounds = plan.rounds;
+
+    const int NQT = n / 4 + 1;
+    const size_t smem = (size_t)NSTAGE * slot * 4 + (size_t)plan.W * NQT * QSTRIDE * 4 + 2 * NSTAGE * sizeof(uint64_t);
+    sweep_launch_fn fn = kLaunch[pde][n - 1];
+    if (!fn) return fail(GPTPINN_E_UNSUPPORTED, "no kernel compiled for pde=%d n=%d", pde, n);
+    if (p.n_items > 0) CUDA_TRY(fn(p, plan.M, plan.ctas, smem, st));
+    if (info) {
+        info->M = plan.M; info->SL = plan.SL; info->W = plan.W; info->items = p.n_items; info->groups = plan.groups;
+        info->ctas = plan.ctas; info->rounds = plan.rounds; info->kernels_launched = p.n_items > 0 ? 2 : 1;
+        info->smem_bytes = (int)smem; info->tiles_per_pass = (int)tiles;
+    }
+    return GPTPINN_OK;
+}
+
+static int check_mat(const gptpinn_mat &m, int n, const char *name)
+{
+    if (!m.ptr) return fail(GPTPINN_E_INVALID, "%s is NULL", name);
+    if (m.ld < n) return fail(GPTPINN_E_INVALID, "%s: ld (%lld) < n (%d)", name, m.ld, n);
+    return GPTPINN_OK;
+}
+static void add_mat(PackJobs &j, const gptpinn_mat &m, long long nrows, int n, int arr, int seg)
+{
+    PackMat &pm = j.mat[j.nmat++];
+    pm.src = m.ptr; pm.ld = m.ld; pm.nrows = nrows; pm.ncols = n; pm.arr = arr; pm.tile0 = seg;   // seg -> tile0 later
+}
+static void add_vec(PackJobs &j, const float *src, long long nrows, int vec, int seg)
+{
+    PackVec &pv = j.vec[j.nvec++];
+    pv.src = src; pv.nrows = nrows; pv.vec = vec; pv.tile0 = seg;
+}
+static int check_common(gptpinn_handle *h, const void *prob, const gptpinn_sweep_args *a, int n, int maxn, int NR, int NI, int NB)
+{
+    if (!h || !prob || !a) return fail(GPTPINN_E_INVALID, "handle, problem and args are required");
+    if (n < 1 || n > maxn) return fail(GPTPINN_E_INVALID, "n = %d outside 1..%d", n, maxn);
+    if (NR < 1 || NI < 1 || NB < 1) return fail(GPTPINN_E_INVALID, "NR, NI, NB must be >= 1");
+    if (a->Np < 0 || (a->Np > 0 && !a->grid_host)) return fail(GPTPINN_E_INVALID, "grid_host NULL or Np < 0");
+    return GPTPINN_OK;
+}
+
+extern "C" int gptpinn_kg_sweep(gptpinn_handle *h, const gptpinn_kg_problem *q, const gptpinn_sweep_args *a,
+                                gptpinn_sweep_info *info, void *stream)
+{
+    int rc = check_common(h, q, a, q ? q->n : 0, kMaxN[PDE_KG], q ? q->NR : 0, q ? q->NI : 0, q ? q->NB : 0);
+    if (rc) return rc;
+    const int n = q->n;
+    if ((rc = check_mat(q->P, n, "P")) || (rc = check_mat(q->Pxx, n, "Pxx")) || (rc = check_mat(q->Ptt, n, "Ptt")) ||
+        (rc = check_mat(q->PIC, n, "PIC")) || (rc = check_mat(q->PICt, n, "PICt")) || (rc = check_mat(q->PBC, n, "PBC")))
+        return rc;
+    if (!q->xcos || !q->ICu1 || !q->BCu) return fail(GPTPINN_E_INVALID, "xcos, ICu1 and BCu are required");
+    PackJobs jobs;
+    memset(&jobs, 0, sizeof(jobs));
+    jobs.narr = PdeTraits<PDE_KG>::NARR;
+    add_mat(jobs, q->Ptt, q->NR, n, 0, 0); add_mat(jobs, q->Pxx, q->NR, n, 1, 0); add_mat(jobs, q->P, q->NR, n, 2, 0);
+    add_vec(jobs, q->xcos, q->NR, 0, 0); add_vec(jobs, q->fhat, q->NR, 1, 0);
+    add_mat(jobs, q->PIC, q->NI, n, 0, 1); add_mat(jobs, q->PICt, q->NI, n, 1, 1);
+    add_vec(jobs, q->ICu1, q->NI, 0, 1); add_vec(jobs, q->ICu2, q->NI, 1, 1);
+    add_mat(jobs, q->PBC, q->NB, n, 0, 2); add_vec(jobs, q->BCu, q->NB, 0, 2);
+    Segments seg; seg.nseg = 3; seg.rows[0] = q->NR; seg.rows[1] = q->NI; seg.rows[2] = q->NB; seg.rows[3] = 0;
+    std::vector<ParamRow> rows((size_t)a->Np);
+    for (int i = 0; i < a->Np; ++i) {
+        const double al = a->grid_host[3 * i], be = a->grid_host[3 * i + 1], ga = a->grid_host[3 * i + 2];
+        rows[i].tp0 = (float)al; rows[i].tp1 = (float)be;
+        rows[i].sp0 = (float)ga; rows[i].sp1 = (float)(2.0 * ga);          // KG_precomp.py:29
+        rows[i].idx = i;
+    }
+    return run_sweep(h, PDE_KG, n, seg, jobs, q->fhat != nullptr, q->NR, q->NI, q->NB, rows, a, info, (cudaStream_t)stream);
+}
+
+extern "C" int gptpinn_b_sweep(gptpinn_handle *h, const gptpinn_b_problem *q, const gptpinn_sweep_args *a,
+                               gptpinn_sweep_info *info, void *stream)
+{
+    int rc = check_common(h, q, a, q ? q->n : 0, kMaxN[PDE_B], q ? q->NR : 0, q ? q->NI : 0, q ? q->NB : 0);
+    if (rc) return rc;
+    const int n = q->n;
+    if ((rc = check_mat(q->P, n, "P")) || (rc = check_mat(q->Px, n, "Px")) || (rc = check_mat(q->Pt, n, "Pt")) ||
+        (rc = check_mat(q->Pxx, n, "Pxx")) || (rc = check_mat(q->PIC, n, "PIC")) || (rc = check_mat(q->PBC, n, "PBC")))
+        return rc;
+    if (!q->ICu) return fail(GPTPINN_E_INVALID, "ICu is required");
+    PackJobs jobs;
+    memset(&jobs, 0, sizeof(jobs));
+    jobs.narr = PdeTraits<PDE_B>::NARR;
+    add_mat(jobs, q->Pt, q->NR, n, 0, 0); add_mat(jobs, q->Pxx, q->NR, n, 1, 0);
+    add_mat(jobs, q->Px, q->NR, n, 2, 0); add_mat(jobs, q->P, q->NR, n, 3, 0);
+    add_vec(jobs, q->fhat, q->NR, 0, 0);
+    add_mat(jobs, q->PIC, q->NI, n, 0, 1); add_vec(jobs, q->ICu, q->NI, 0, 1);
+    add_mat(jobs, q->PBC, q->NB, n, 0, 2); add_vec(jobs, q->BCu, q->NB, 0, 2);
+    Segments seg; seg.nseg = 3; seg.rows[0] = q->NR; seg.rows[1] = q->NI; seg.rows[2] = q->NB; seg.rows[3] = 0;
+    std::vector<ParamRow> rows((size_t)a->Np);
+    for (int i = 0; i < a->Np; ++i) {
+        rows[i].tp0 = (float)(-a->grid_host[i]); rows[i].tp1 = 0.f;       // B_precomp.py:19
+        rows[i].sp0 = 0.f; rows[i].sp1 = 0.f; rows[i].idx = i;
+    }
+    return run_sweep(h, PDE_B, n, seg, jobs, q->fhat != nullptr, q->NR, q->NI, q->NB, rows, a, info, (cudaStream_t)stream);
+}
+
+extern "C" int gptpinn_ac_sweep(gptpinn_handle *h, const gptpinn_ac_problem *q, const gptpinn_sweep_args *a,
+                                gptpinn_sweep_info *info, void *stream)
+{
+    int rc = check_common(h, q, a, q ? q->n : 0, kMaxN[PDE_AC], q ? q->NR : 0, q ? q->NI : 0, q ? q->NB : 0);
+    if (rc) return rc;
+    const int n = q->n;
+    if ((rc = check_mat(q->P, n, "P")) || (rc = check_mat(q->Pt, n, "Pt")) || (rc = check_mat(q->Pxx, n, "Pxx")) ||
+        (rc = check_mat(q->PIC, n, "PIC")) || (rc = check_mat(q->Pub, n, "Pub")) || (rc = check_mat(q->Plb, n, "Plb")) ||
+        (rc = check_mat(q->Pdiff, n, "Pdiff")) || (rc = check_mat(q->Pubx, n, "Pubx")) ||
+        (rc = check_mat(q->Plbx, n, "Plbx")) || (rc = check_mat(q->Pdiffx, n, "Pdiffx")))
+        return rc;
+    if (!q->ICu) return fail(GPTPINN_E_INVALID, "ICu is required");
+    PackJobs jobs;
+    memset(&jobs, 0, sizeof(jobs));
+    jobs.narr = PdeTraits<PDE_AC>::NARR;
+    add_mat(jobs, q->Pt, q->NR, n, 0, 0); add_mat(jobs, q->Pxx, q->NR, n, 1, 0); add_mat(jobs, q->P, q->NR, n, 2, 0);
+    add_vec(jobs, q->fhat, q->NR, 0, 0);
+    add_mat(jobs, q->PIC, q->NI, n, 0, 1); add_vec(jobs, q->ICu, q->NI, 0, 1);
+    add_mat(jobs, q->Pub, q->NB, n, 0, 2); add_mat(jobs, q->Plb, q->NB, n, 1, 2); add_mat(jobs, q->Pdiff, q->NB, n, 2, 2);
+    add_mat(jobs, q->Pubx, q->NB, n, 0, 3); add_mat(jobs, q->Plbx, q->NB, n, 1, 3); add_mat(jobs, q->Pdiffx, q->NB, n, 2, 3);
+    Segments seg; seg.nseg = 4; seg.rows[0] = q->NR; seg.rows[1] = q->NI; seg.rows[2] = q->NB; seg.rows[3] = q->NB;
+    std::vector<ParamRow> rows((size_t)a->Np);
+    for (int i = 0; i < a->Np; ++i) {
+        const double lam = a->grid_host[2 * i], eps = a->grid_host[2 * i + 1];
+        rows[i].tp0 = (float)(-lam); rows[i].tp1 = (float)(-eps);       // AC_precompute.py:21-22
+        rows[i].sp0 = (float)eps; rows[i].sp1 = (float)(3.0 * eps);     // AC_optimizer.py:42,45
+        rows[i].idx = i;
+    }
+    return run_sweep(h, PDE_AC, n, seg, jobs, q->fhat != nullptr, q->NR, q->NI, q->NB, rows, a, info, (cudaStream_t)stream);
+}
+
+extern "C" int gptpinn_argmax_scan(const float *f_dev, const float *m_dev, int Np, float *L_out_dev, int *idx_out_dev, void *stream)
+{
+    if (!f_dev || !m_dev || !L_out_dev || !idx_out_dev || Np < 0) return fail(GPTPINN_E_INVALID, "gptpinn_argmax_scan: bad arguments");
+    CUDA_TRY(launch_argmax_scan(f_dev, m_dev, Np, L_out_dev, idx_out_dev, (cudaStream_t)stream));
+    return GPTPINN_OK;
+}
+
+extern "C" int gptpinn_mlp_channels(const gptpinn_mlp *mlp, const float *xt_dev, long long N,
+                                    float *const out_dev[5], const long long ld[5], void *stream)
+{
+    if (!mlp || !xt_dev || !out_dev || !ld || N < 0) return fail(GPTPINN_E_INVALID, "gptpinn_mlp_channels: bad arguments");
+    if (mlp->nlayers < 2 || mlp->nlayers > MLP_MAX_LAYERS) return fail(GPTPINN_E_INVALID, "nlayers = %d outside 2..%d", mlp->nlayers, MLP_MAX_LAYERS);
+    if (mlp->layers[0] != 2 || mlp->layers[mlp->nlayers - 1] != 1) return fail(GPTPINN_E_INVALID, "network must map 2 inputs to 1 output");
+    if (mlp->act != GPTPINN_ACT_COS && mlp->act != GPTPINN_ACT_TANH) return fail(GPTPINN_E_INVALID, "unknown activation %d", mlp->act);
+    MlpDesc d;
+    memset(&d, 0, sizeof(d));
+    d.nlayers = mlp->nlayers; d.act = mlp->act;
+    for (int l = 0; l < mlp->nlayers; ++l) {
+        d.layers[l] = mlp->layers[l];
+        if (d.layers[l] < 1 || d.layers[l] > 128) return fail(GPTPINN_E_UNSUPPORTED, "layer width %d outside 1..128", d.layers[l]);
+    }
+    for (int l = 0; l < mlp->nlayers - 1; ++l) {
+        if (!mlp->W[l] || !mlp->b[l]) return fail(GPTPINN_E_INVALID, "W[%d] or b[%d] is NULL", l, l);
+        d.W[l] = mlp->W[l]; d.b[l] = mlp->b[l];
+    }
+    MlpOut o;
+    bool any = false;
+    for (int c = 0; c < 5; ++c) { o.ptr[c] = out_dev[c]; o.ld[c] = ld[c]; any = any || out_dev[c]; }
+    if (!any) return GPTPINN_OK;
+    CUDA_TRY(launch_mlp_channels(d, xt_dev, N, o, (cudaStream_t)stream));
+    return GPTPINN_OK;
+}

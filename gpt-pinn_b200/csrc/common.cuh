@@ -1,0 +1,116 @@
+// common.cuh -- shared definitions for the sm_100a GPT-PINN kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gp {
+
+// ----------------------------------------------------------------------------------------
+// Packed activation stream ("mirror") layout.
+//
+// The reference keeps P, P_xx, ... as [N, number_of_neurons] row-major buffers and hands the
+// sweep column-slice views (row stride 15 floats = 60 B: not 16-B aligned, so not TMA-able,
+// SURVEY.md H4).  The pack kernel rewrites them once per sweep call into a tile stream:
+//
+//   stream = tile[0] tile[1] ... tile[tiles_per_pass-1]        (segment after segment)
+//   tile   = NARR matrix blocks, then NVEC row vectors          (SLOT floats, 16-B multiple)
+//   matrix block = [4 column-quads][R_TILE rows][4 floats]      (k = 4*quad + lane component)
+//   row vector   = [R_TILE]
+//
+// so that (a) one tile is ONE contiguous cp.async.bulk (TMA bulk copy) into shared memory,
+// (b) a thread reads 4 neurons of one row with one LDS.128, and (c) the row-slices of a warp
+// touch consecutive 16-B chunks (bank-conflict free), while lanes that share a row broadcast.
+// Rows past N and columns past n are zero, which contributes nothing to any sum.
+// ----------------------------------------------------------------------------------------
+constexpr int R_TILE   = 64;                 // rows per tile
+constexpr int QSTRIDE  = R_TILE * 4;         // floats in one column-quad plane
+constexpr int ARR_FLTS = 4 * QSTRIDE;        // one matrix block (16 columns)
+constexpr int NSTAGE   = 4;                  // shared-memory ring depth
+constexpr int LOOKAHEAD = 2;                 // tiles in flight ahead of the consumers
+constexpr int MAX_SEG  = 4;
+
+constexpr int PDE_KG = 0, PDE_B = 1, PDE_AC = 2;
+
+template <int PDE> struct PdeTraits;
+template <> struct PdeTraits<PDE_KG> {      // residual: Ptt,Pxx,P | xcos,fhat ; IC: PIC,PICt | u1,u2 ; BC: PBC | BCu
+    static constexpr int NARR = 3, NVEC = 2, NSEG = 3, TARR = 1;   // TARR: # per-warp derived blocks
+};
+template <> struct PdeTraits<PDE_B> {       // residual: Pt,Pxx,Px,P | fhat ; IC: PIC | ICu ; BC: PBC | BCu
+    static constexpr int NARR = 4, NVEC = 1, NSEG = 3, TARR = 1;
+};
+template <> struct PdeTraits<PDE_AC> {      // residual: Pt,Pxx,P | fhat ; IC: PIC | ICu ; BC: Pub,Plb,Pdiff ; BCx: Pubx,Plbx,Pdiffx
+    static constexpr int NARR = 3, NVEC = 1, NSEG = 4, TARR = 1;
+};
+template <int PDE> struct SlotFloats { static constexpr int value = PdeTraits<PDE>::NARR * ARR_FLTS + PdeTraits<PDE>::NVEC * R_TILE; };
+
+struct ItemDesc {          // one warp work item: a set of parameters that share the same T
+    float tp0, tp1;        // KG: alpha, beta    B: -nu, 0      AC: -lambda, -eps
+    int   sib_start;       // first sibling in SibDesc[]
+    int   sib_count;       // 1 .. SL*M
+    int   SL;              // sibling lanes of this item (power of two); row slices RL = 32/SL
+    int   pad[3];
+};
+struct SibDesc {
+    float sp0, sp1;        // KG: gamma, 2*gamma  B: 0,0        AC: eps, 3*eps
+    int   out_idx;         // row of the caller's grid
+    int   pad;
+};
+
+struct SweepParams {
+    const float   *packed;           // tile stream
+    int            ntile[MAX_SEG];   // tiles per segment
+    int            tiles_per_pass;
+    float          nR, nI, nB;       // sizes as float (loss means)
+    float          fac1, fac2, fac3; // (float)(2/NR), (float)(2/NB), (float)(2/NI)
+    float          lr;
+    int            epochs, rec_every, nrec;
+    int            has_fhat;
+    const ItemDesc *items;
+    int            n_items;
+    const SibDesc  *sibs;
+    const float    *c0;
+    int            c0_per_param;
+    float          *c_out, *f_out, *m_out, *trace;
+    int            W;                // warps per CTA
+    int            rounds;
+};
+
+// ---- PTX wrappers: mbarrier + TMA bulk copy --------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    const uint32_t a = smem_u32(bar);
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+}  // namespace gp

@@ -1,0 +1,32 @@
+// pack.cuh -- host-visible descriptors of the pack and scan kernels.
+#pragma once
+#include "common.cuh"
+
+namespace gp {
+
+struct PackMat {
+    const float *src;      // device, row-major, row stride ld
+    long long    ld;
+    long long    nrows;
+    int          ncols;    // n
+    int          arr;      // matrix block index inside the tile slot
+    long long    tile0;    // first tile of the segment this matrix belongs to
+};
+struct PackVec {
+    const float *src;      // device [nrows] or nullptr (leave zeros)
+    long long    nrows;
+    int          vec;      // row-vector index inside the tile slot
+    long long    tile0;
+};
+struct PackJobs {
+    PackMat mat[12];
+    PackVec vec[8];
+    int     nmat, nvec;
+    int     narr;          // matrix blocks per slot
+    long long slot;        // floats per slot
+};
+
+cudaError_t launch_pack(const PackJobs &jobs, float *stream, long long max_rows, cudaStream_t st);
+cudaError_t launch_argmax_scan(const float *f, const float *m, int Np, float *L_out, int *idx_out, cudaStream_t st);
+
+}  // namespace gp

@@ -1,0 +1,12 @@
+// sweep_inst.cu -- one translation unit per (PDE, n): compiled with -DGP_PDE=<0|1|2> -DGP_N=<n>.
+#include "sweep_kernel.cuh"
+
+#define GP_CAT2(a, b, c) a##b##_##c
+#define GP_CAT(a, b, c) GP_CAT2(a, b, c)
+
+namespace gp {
+cudaError_t GP_CAT(sweep_launch_, GP_PDE, GP_N)(const SweepParams &p, int M, int ctas, size_t smem, cudaStream_t st)
+{
+    return launch_n<GP_PDE, GP_N>(p, M, ctas, smem, st);
+}
+}  // namespace gp

@@ -1,0 +1,121 @@
+"""ctypes binding of libgptpinn_b200.so (C ABI: include/gptpinn_b200.h).
+
+There is no fallback of any kind: if the shared library is missing or the device is not a
+B200-class (sm_100) GPU the import / first call raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgptpinn_b200.so")
+
+_fp = C.POINTER(C.c_float)
+
+
+class Mat(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("ld", C.c_longlong)]
+
+
+class KGProblem(C.Structure):
+    _fields_ = [("n", C.c_int), ("NR", C.c_int), ("NI", C.c_int), ("NB", C.c_int),
+                ("P", Mat), ("Pxx", Mat), ("Ptt", Mat), ("PIC", Mat), ("PICt", Mat), ("PBC", Mat),
+                ("xcos", C.c_void_p), ("fhat", C.c_void_p), ("ICu1", C.c_void_p), ("ICu2", C.c_void_p),
+                ("BCu", C.c_void_p)]
+
+
+class BProblem(C.Structure):
+    _fields_ = [("n", C.c_int), ("NR", C.c_int), ("NI", C.c_int), ("NB", C.c_int),
+                ("P", Mat), ("Px", Mat), ("Pt", Mat), ("Pxx", Mat), ("PIC", Mat), ("PBC", Mat),
+                ("fhat", C.c_void_p), ("ICu", C.c_void_p), ("BCu", C.c_void_p)]
+
+
+class ACProblem(C.Structure):
+    _fields_ = [("n", C.c_int), ("NR", C.c_int), ("NI", C.c_int), ("NB", C.c_int),
+                ("P", Mat), ("Pt", Mat), ("Pxx", Mat), ("PIC", Mat),
+                ("Pub", Mat), ("Plb", Mat), ("Pdiff", Mat), ("Pubx", Mat), ("Plbx", Mat), ("Pdiffx", Mat),
+                ("fhat", C.c_void_p), ("ICu", C.c_void_p)]
+
+
+class SweepArgs(C.Structure):
+    _fields_ = [("grid_host", C.POINTER(C.c_double)), ("Np", C.c_int),
+                ("c0_dev", C.c_void_p), ("c0_per_param", C.c_int),
+                ("epochs", C.c_int), ("lr", C.c_double), ("rec_every", C.c_int),
+                ("c_out_dev", C.c_void_p), ("f_out_dev", C.c_void_p), ("m_out_dev", C.c_void_p),
+                ("trace_dev", C.c_void_p),
+                ("cfg_M", C.c_int), ("cfg_SL", C.c_int), ("cfg_W", C.c_int)]
+
+
+class SweepInfo(C.Structure):
+    _fields_ = [("M", C.c_int), ("SL", C.c_int), ("W", C.c_int), ("items", C.c_int), ("groups", C.c_int),
+                ("ctas", C.c_int), ("rounds", C.c_int), ("kernels_launched", C.c_int),
+                ("smem_bytes", C.c_int), ("tiles_per_pass", C.c_int)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Mlp(C.Structure):
+    _fields_ = [("nlayers", C.c_int), ("layers", C.c_int * 8), ("W", C.c_void_p * 7), ("b", C.c_void_p * 7),
+                ("act", C.c_int)]
+
+
+EXPORTS = ("gptpinn_version", "gptpinn_last_error", "gptpinn_create", "gptpinn_destroy",
+           "gptpinn_kg_sweep", "gptpinn_b_sweep", "gptpinn_ac_sweep", "gptpinn_argmax_scan",
+           "gptpinn_mlp_channels", "gptpinn_ffma_peak")
+
+_lib = None
+
+
+class GptPinnError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GptPinnError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C gpt-pinn_b200/csrc`.  There is no CPU / PyTorch fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.gptpinn_version.restype = C.c_int
+    L.gptpinn_last_error.restype = C.c_char_p
+    L.gptpinn_create.argtypes = [C.POINTER(C.c_void_p)]
+    L.gptpinn_destroy.argtypes = [C.c_void_p]
+    for name, prob in (("gptpinn_kg_sweep", KGProblem), ("gptpinn_b_sweep", BProblem),
+                       ("gptpinn_ac_sweep", ACProblem)):
+        fn = getattr(L, name)
+        fn.argtypes = [C.c_void_p, C.POINTER(prob), C.POINTER(SweepArgs), C.POINTER(SweepInfo), C.c_void_p]
+        fn.restype = C.c_int
+    L.gptpinn_argmax_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gptpinn_argmax_scan.restype = C.c_int
+    L.gptpinn_mlp_channels.argtypes = [C.POINTER(Mlp), C.c_void_p, C.c_longlong, C.POINTER(C.c_void_p * 5),
+                                       C.POINTER(C.c_longlong * 5), C.c_void_p]
+    L.gptpinn_mlp_channels.restype = C.c_int
+    L.gptpinn_ffma_peak.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_void_p]
+    L.gptpinn_ffma_peak.restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().gptpinn_last_error().decode("utf-8", "replace")
+        raise GptPinnError(f"{what} failed (code {rc}): {msg}")
+
+
+_handles = {}
+
+
+def handle(device_index):
+    """Per-device workspace handle (created lazily; lives for the process)."""
+    import torch
+    h = _handles.get(device_index)
+    if h is None:
+        with torch.cuda.device(device_index):
+            hp = C.c_void_p()
+            check(lib().gptpinn_create(C.byref(hp)), "gptpinn_create")
+        _handles[device_index] = h = hp
+    return h

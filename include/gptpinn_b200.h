@@ -1,0 +1,180 @@
+/*
+ * gptpinn_b200.h -- C ABI of libgptpinn_b200.so: the B200 (sm_100a) implementation of the
+ * GPT-PINN data-parallel hot path (greedy offline coefficient sweep, its feeder precompute
+ * and the grid arg-max).
+ *
+ * The reference (skoohy/GPT-PINN) is pure Python on PyTorch and has no FFI layer; its
+ * boundary for this path is the set of Python functions that *_main.py imports.  Each entry
+ * point below names the reference interface it replaces (file:line relative to the
+ * reference root).  The Python drop-in modules (gpt-pinn_b200/dropin/KG_train.py ...) bind
+ * these symbols with ctypes; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - all `*_dev` / gptpinn_mat pointers are DEVICE pointers on the current CUDA device,
+ *     fp32; all `*_host` pointers are host pointers; nothing is retained after return.
+ *   - matrices are row-major with an explicit row stride `ld` (floats): the reference hands
+ *     over column-slice views `out[:, 0:n]` of [N, number_of_neurons] buffers
+ *     (Klein-Gordon/KG_precomp.py:51-52), so ld != n in general.  Vectors ([N,1] tensors in
+ *     the reference) are contiguous.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls enqueue
+ *     work and return; they synchronise only where stated.
+ *   - every function returns GPTPINN_OK (0) or a negative GPTPINN_E_* code and never throws;
+ *     gptpinn_last_error() gives the message of the last failure on the calling thread.
+ *   - scalars that the reference multiplies into fp32 tensors (alpha, beta, gamma, 2*gamma,
+ *     nu, lambda, eps, 3*eps, 2/N, lr) are taken as double and rounded to fp32 at the same
+ *     points the reference rounds them.
+ */
+#ifndef GPTPINN_B200_H
+#define GPTPINN_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPTPINN_OK              0
+#define GPTPINN_E_INVALID      -1   /* bad argument (null pointer, n out of range, ...)        */
+#define GPTPINN_E_CUDA         -2   /* a CUDA runtime call failed                               */
+#define GPTPINN_E_UNSUPPORTED  -3   /* device is not sm_100 / configuration not compiled        */
+#define GPTPINN_E_NOMEM        -4
+
+#define GPTPINN_MAX_NEURONS    15   /* KG uses 15, Burgers / Allen-Cahn 9                       */
+
+typedef struct gptpinn_handle gptpinn_handle;   /* per-device workspace owner (opaque)        */
+
+typedef struct {
+    const float *ptr;      /* device, fp32                                                     */
+    long long    ld;       /* row stride in floats                                             */
+} gptpinn_mat;
+
+/* Klein-Gordon reduced problem: everything KG_optimizer.grad_descent.__init__
+ * (Klein-Gordon/KG_optimizer.py:4-32) and KG_models.GPT.__init__ (KG_models.py:8-26) keep.    */
+typedef struct {
+    int n;                               /* neurons in use, 1..15                              */
+    int NR, NI, NB;                      /* xt_size, IC_size, BC_size                          */
+    gptpinn_mat P, Pxx, Ptt;             /* out, out_xx, out_tt           [NR, n]              */
+    gptpinn_mat PIC, PICt;               /* out_IC, out_IC_t              [NI, n]              */
+    gptpinn_mat PBC;                     /* out_BC                        [NB, n]              */
+    const float *xcos;                   /* xcos_x2cos2                   [NR]                 */
+    const float *fhat;                   /* f_hat [NR], or NULL == all zero                    */
+    const float *ICu1, *ICu2;            /* IC_u1, IC_u2 [NI]; ICu2 NULL == all zero           */
+    const float *BCu;                    /* BC_u  [NB]                                         */
+} gptpinn_kg_problem;
+
+/* Burgers: B_optimizer.py:4-26, B_models.py:12-26                                             */
+typedef struct {
+    int n;
+    int NR, NI, NB;
+    gptpinn_mat P, Px, Pt, Pxx;          /* out, out_x, out_t, out_xx     [NR, n]              */
+    gptpinn_mat PIC;                     /* out_IC                        [NI, n]              */
+    gptpinn_mat PBC;                     /* out_BC                        [NB, n]              */
+    const float *fhat;                   /* [NR] or NULL                                       */
+    const float *ICu;                    /* [NI]                                               */
+    const float *BCu;                    /* [NB] or NULL (used by the loss only, N3)           */
+} gptpinn_b_problem;
+
+/* Allen-Cahn: AC_optimizer.py:4-34, AC_models.py:13-29                                        */
+typedef struct {
+    int n;
+    int NR, NI, NB;
+    gptpinn_mat P, Pt, Pxx;              /* out, out_t, out_xx            [NR, n]              */
+    gptpinn_mat PIC;                     /* out_IC                        [NI, n]              */
+    gptpinn_mat Pub, Plb, Pdiff;         /* out_BC_ub/lb/diff             [NB, n]              */
+    gptpinn_mat Pubx, Plbx, Pdiffx;      /* out_BC_ub_x/lb_x/diff_x       [NB, n]              */
+    const float *fhat;                   /* [NR] or NULL                                       */
+    const float *ICu;                    /* [NI]                                               */
+} gptpinn_ac_problem;
+
+/* What one sweep call does for each of the Np grid rows (parameters):
+ *     c <- c0;  for j = 0..epochs:  loss_j = GPT.loss(c);  if j < epochs: c <- update(c)
+ * i.e. the loop of offline_generation (Klein-Gordon/KG_train.py:27-37, Burgers/B_train.py:60-67,
+ * Allen-Cahn/AC_train.py:24-31) without its early exit, which is also the loop of gpt_test /
+ * gpt_test_loss (KG_test.py:30-32, 67-72).  Per parameter it returns
+ *     c_out[p,:]   = c after `epochs` updates                           (may be NULL)
+ *     f_out[p]     = loss_epochs                                        (the "final loss")
+ *     m_out[p]     = min_{0 <= j < epochs} loss_j                       (early-exit witness)
+ *     trace[p, j/rec_every] = loss_j for j % rec_every == 0             (NULL or rec_every<=0: off)
+ * from which gptpinn_argmax_scan reproduces offline_generation's (largest_loss, largest_case)
+ * exactly.                                                                     */
+typedef struct {
+    const double *grid_host;   /* [Np, 3] (KG: alpha,beta,gamma) / [Np] (B: nu) / [Np,2] (AC: lambda,eps) */
+    int           Np;
+    const float  *c0_dev;      /* [n] shared by all parameters, or [Np, n] when c0_per_param   */
+    int           c0_per_param;
+    int           epochs;
+    double        lr;
+    int           rec_every;
+    float        *c_out_dev;   /* [Np, n] or NULL                                              */
+    float        *f_out_dev;   /* [Np]                                                         */
+    float        *m_out_dev;   /* [Np]                                                         */
+    float        *trace_dev;   /* [Np, epochs/rec_every + 1] or NULL                           */
+    /* tuning override, 0 = let the library choose: parameters per thread (M), sibling lanes
+     * per warp (SL, power of two <= 32), warps per CTA (W).                                   */
+    int           cfg_M, cfg_SL, cfg_W;
+} gptpinn_sweep_args;
+
+/* filled by the sweep calls when non-NULL: what was launched (for bench.py / tests)           */
+typedef struct {
+    int   M, SL, W;            /* chosen configuration                                         */
+    int   items;               /* warp work items                                              */
+    int   groups;              /* distinct T-parameter groups found in the grid                */
+    int   ctas, rounds;
+    int   kernels_launched;    /* sweep + pack kernels enqueued by this call                   */
+    int   smem_bytes;
+    int   tiles_per_pass;
+} gptpinn_sweep_info;
+
+int  gptpinn_version(void);
+const char *gptpinn_last_error(void);
+
+/* handle = workspace owner for one device (packed activation mirror, work-item tables)        */
+int  gptpinn_create(gptpinn_handle **out);
+int  gptpinn_destroy(gptpinn_handle *h);
+
+/* replaces the per-parameter body of offline_generation / gpt_test / gpt_test_loss:
+ * KG_train.py:14-37 + KG_optimizer.py:34-68 + KG_models.py:28-50 + KG_precomp.py:23-29        */
+int  gptpinn_kg_sweep(gptpinn_handle *h, const gptpinn_kg_problem *prob,
+                      const gptpinn_sweep_args *args, gptpinn_sweep_info *info, void *stream);
+/* B_train.py:49-67 + B_optimizer.py:28-58 + B_models.py:28-46 + B_precomp.py:18-20            */
+int  gptpinn_b_sweep(gptpinn_handle *h, const gptpinn_b_problem *prob,
+                     const gptpinn_sweep_args *args, gptpinn_sweep_info *info, void *stream);
+/* AC_train.py:12-31 + AC_optimizer.py:36-66 + AC_models.py:31-54 + AC_precompute.py:20-24     */
+int  gptpinn_ac_sweep(gptpinn_handle *h, const gptpinn_ac_problem *prob,
+                      const gptpinn_sweep_args *args, gptpinn_sweep_info *info, void *stream);
+
+/* Exact arg-max of offline_generation (KG_train.py:12,31-41; B_train.py:18,62-70;
+ * AC_train.py:10,25-38) from the two per-parameter scalars: visits p = 0..Np-1 in order with
+ * running maximum L (initially 0) and sets (L, idx) <- (f[p], p) iff !(m[p] < L) && f[p] > L.
+ * Writes L to L_out_dev[0] and the winning index (-1 if none) to idx_out_dev[0].              */
+int  gptpinn_argmax_scan(const float *f_dev, const float *m_dev, int Np,
+                         float *L_out_dev, int *idx_out_dev, void *stream);
+
+/* Pre-trained full-PINN activation network (reference classes KG_models.NN, B_models.NN,
+ * AC_models.P): layers[0] = 2 inputs (x,t), tanh or cos hidden activations, linear output.    */
+#define GPTPINN_ACT_COS   0     /* Klein-Gordon/KG_models.py:56-60                              */
+#define GPTPINN_ACT_TANH  1     /* Burgers/B_models.py:69, Allen-Cahn/AC_models.py:68           */
+typedef struct {
+    int          nlayers;       /* entries of `layers`, <= 8                                     */
+    int          layers[8];
+    const float *W[7];          /* device, nn.Linear.weight  [layers[l+1], layers[l]] row-major  */
+    const float *b[7];          /* device, nn.Linear.bias    [layers[l+1]]                       */
+    int          act;
+} gptpinn_mlp;
+
+/* Closed-form replacement of the autograd calls in inputs() (KG_precomp.py:7-21 and 34-52,
+ * B_precomp.py:6-16, AC_precompute.py:7-18): evaluates, at N points xt_dev[N,2], the channels
+ *   out[0] = u, out[1] = u_x, out[2] = u_t, out[3] = "P_xx" = u_xx + u_xt, out[4] = "P_tt" =
+ *   u_tt + u_xt  (the mixed-derivative semantics of the reference)
+ * and writes channel c of point p to out_dev[c][p * ld[c]]; out_dev[c] == NULL skips it.  With
+ * ld = number_of_neurons and out_dev[c] = &buffer[0][i] this fills column i in place.          */
+int  gptpinn_mlp_channels(const gptpinn_mlp *mlp, const float *xt_dev, long long N,
+                          float *const out_dev[5], const long long ld[5], void *stream);
+
+/* FFMA-only microbenchmark on the current device: best-of-`reps` FP32 CUDA-core throughput in
+ * TFLOP/s (2 flop per FMA).  It is the measured denominator of the sweep kernel's roofline;
+ * it has no counterpart in the reference.  Synchronises the stream.                            */
+int  gptpinn_ffma_peak(double *tflops_out, int reps, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPTPINN_B200_H */

@@ -1,0 +1,212 @@
+#!/usr/bin/env python
+"""Generate golden fixtures by running the UNMODIFIED reference (skoohy/GPT-PINN) on CPU.
+
+TEST INFRASTRUCTURE ONLY.  Runs in the build container (needs /root/reference, which does
+not exist on the GPU box); its outputs are committed under tests/golden/*.npz and are what
+pins both the oracle restatement (oracle/) and the CUDA path.
+
+How the reference is driven:
+  * the reference folder is put on sys.path and its modules imported as-is;
+  * the module attribute `device` (hard-coded torch.device("cuda")) is re-bound to cpu;
+  * synthetic full-PINN "neurons" are random MLPs of the reference architecture pushed
+    through the reference's own `inputs()` (KG_precomp.py:34-52, B_precomp.py:22-55,
+    AC_precompute.py:26-58), so the activation matrices carry the reference's mixed
+    second-derivative semantics;
+  * per-parameter trajectories come from the reference classes `grad_descent.update`
+    (KG_optimizer.py:34-68 ...) and `GPT.loss` (KG_models.py:45-50 ...), driven by the
+    same loop as `offline_generation` (KG_train.py:27-37) without the early exit;
+  * `(largest_loss, largest_case)` come from the reference `offline_generation` itself,
+    and the test sweeps from `gpt_test` / `gpt_test_loss`.
+
+Usage:  python oracle/gen_golden.py [kg_small|kg_full|b_small|ac_small|kg_precomp|...|all]
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = os.environ.get("GPTPINN_REFERENCE", "/root/reference")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+CPU = torch.device("cpu")
+
+
+def _import_ref(folder, names):
+    path = os.path.join(REF, folder)
+    if path not in sys.path:
+        sys.path.insert(0, path)
+    mods = {}
+    for n in names:
+        m = importlib.import_module(n)
+        if hasattr(m, "device"):
+            m.device = CPU
+        mods[n] = m
+    return mods
+
+
+def _randomize(pinn, seed, scale=0.6, pert=0.05):
+    """Seeded synthetic weights: Xavier-normal x scale + N(0, pert^2), zero bias."""
+    g = torch.Generator().manual_seed(seed)
+    for lin in pinn.linears:
+        fan_out, fan_in = lin.weight.shape
+        std = (2.0 / (fan_in + fan_out)) ** 0.5
+        w = torch.randn(lin.weight.shape, generator=g) * std * scale
+        w = w + torch.randn(lin.weight.shape, generator=g) * pert
+        lin.weight.data = w.float()
+        lin.bias.data = torch.zeros_like(lin.bias.data)
+
+
+def _weights(pinn):
+    out = {}
+    for li, lin in enumerate(pinn.linears):
+        out[f"W{li}"] = lin.weight.data.numpy().copy()
+        out[f"b{li}"] = lin.bias.data.numpy().copy()
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# Klein-Gordon
+# --------------------------------------------------------------------------------------
+def kg_problem(Nc, IC_pts, BC_pts, N_test, nmax, seed0=1000):
+    m = _import_ref("Klein-Gordon", ["KG_data", "KG_models", "KG_precomp", "KG_optimizer",
+                                     "KG_train", "KG_test"])
+    xt_resid, f_hat, xt_test = m["KG_data"].residual_data(-1.0, 1.0, 0.0, 5.0, Nc, N_test)
+    IC_xt, IC_u1, IC_u2, BC_xt, BC_u = m["KG_data"].ICBC_data(-1.0, 1.0, 0.0, 5.0, BC_pts, IC_pts)
+    xcos = m["KG_precomp"].xcos_term(xt_resid[:, 0].unsqueeze(1), xt_resid[:, 1].unsqueeze(1))
+    xt_resid = xt_resid.requires_grad_()
+    IC_xt = IC_xt.requires_grad_()
+    N, NI, NB, NT = xt_resid.shape[0], IC_xt.shape[0], BC_xt.shape[0], xt_test.shape[0]
+    bufs = dict(out=torch.ones(N, nmax), out_xx=torch.ones(N, nmax), out_tt=torch.ones(N, nmax),
+                out_IC=torch.ones(NI, nmax), out_IC_t=torch.ones(NI, nmax),
+                out_BC=torch.ones(NB, nmax), out_test=torch.zeros(NT, nmax))
+    layers = np.array([2, 40, 40, 1])
+    weights = []
+    for i in range(nmax):
+        pinn = m["KG_models"].NN(layers, -1.5, 0.5, 0.5, xcos)
+        _randomize(pinn, seed0 + i)
+        weights.append(_weights(pinn))
+        m["KG_precomp"].inputs(pinn, xt_resid, bufs["out"], bufs["out_xx"], bufs["out_tt"],
+                               bufs["out_IC_t"], bufs["out_IC"], bufs["out_BC"], IC_xt, BC_xt,
+                               i, bufs["out_test"], xt_test)
+    bufs = {k: v.detach() for k, v in bufs.items()}
+    return m, dict(xt_resid=xt_resid.detach(), xt_test=xt_test, IC_xt=IC_xt.detach(), BC_xt=BC_xt,
+                   IC_u1=IC_u1, IC_u2=IC_u2, BC_u=BC_u, f_hat=f_hat, xcos=xcos.detach(),
+                   weights=weights, **bufs)
+
+
+def kg_trajectories(m, p, grid, n, epochs, lr, rec_every):
+    """Per-mu: c_final, final loss f_p, min-prefix loss m_p, loss trace (KG_train.py:27-37 loop)."""
+    v = {k: p[k][:, :n] for k in ("out", "out_xx", "out_tt", "out_IC", "out_IC_t", "out_BC")}
+    N, NI, NB = p["out"].shape[0], p["out_IC"].shape[0], p["out_BC"].shape[0]
+    c0 = torch.full((n,), 1.0 / n)
+    nrec = epochs // rec_every + 1
+    C = np.zeros((len(grid), n), np.float32)
+    F = np.zeros(len(grid), np.float32)
+    M = np.zeros(len(grid), np.float32)
+    T = np.zeros((len(grid), nrec), np.float32)
+    for gi, (a, b, g) in enumerate(grid):
+        Tt = m["KG_precomp"].Ptt_aPxx_bP(a, b, v["out_tt"], v["out_xx"], v["out"])
+        G2 = m["KG_precomp"].gamma2_P(g, v["out"])
+        GD = m["KG_optimizer"].grad_descent(a, b, g, N, NI, NB, p["IC_u1"], p["IC_u2"], p["BC_u"],
+                                            p["xcos"], Tt, G2, v["out"], v["out_IC"],
+                                            v["out_IC_t"], v["out_BC"], epochs, lr)
+        NNg = m["KG_models"].GPT(a, b, g, v["out"], v["out_IC"], v["out_IC_t"], v["out_BC"],
+                                 p["xcos"], p["f_hat"], Tt, p["IC_u1"], p["IC_u2"], p["BC_u"])
+        c = c0
+        cr = c.unsqueeze(1)
+        loss = NNg.loss(cr)
+        mp = float("inf")
+        T[gi, 0] = loss.item()
+        for j in range(1, epochs + 1):
+            mp = min(mp, loss.item())          # min over l_0 .. l_{E-1}
+            c = GD.update(c, cr)
+            cr = c.unsqueeze(1)
+            loss = NNg.loss(cr)
+            if j % rec_every == 0:
+                T[gi, j // rec_every] = loss.item()
+        C[gi] = c.numpy()
+        F[gi] = loss.item()
+        M[gi] = mp
+    return C, F, M, T
+
+
+def kg_case(tag, Nc, IC_pts, BC_pts, N_test, ns, grid, epochs, lr, rec_every, test_mu, test_epochs,
+            nmax=15):
+    m, p = kg_problem(Nc, IC_pts, BC_pts, N_test, nmax)
+    N, NI, NB = p["out"].shape[0], p["out_IC"].shape[0], p["out_BC"].shape[0]
+    save = {k: p[k].numpy() for k in ("xt_resid", "xt_test", "IC_xt", "BC_xt", "IC_u1", "IC_u2",
+                                      "BC_u", "f_hat", "xcos", "out", "out_xx", "out_tt", "out_IC",
+                                      "out_IC_t", "out_BC", "out_test")}
+    for i, w in enumerate(p["weights"]):
+        for k, a in w.items():
+            save[f"pinn{i}_{k}"] = a
+    lrs = lr if isinstance(lr, dict) else {n: lr for n in ns}
+    save.update(grid=grid, ns=np.array(ns), epochs=epochs, lr=np.array([lrs[n] for n in ns]),
+                rec_every=rec_every)
+    for n in ns:
+        lr = lrs[n]
+        C, F, M, T = kg_trajectories(m, p, grid, n, epochs, lr, rec_every)
+        v = {k: p[k][:, :n] for k in ("out", "out_xx", "out_tt", "out_IC", "out_IC_t", "out_BC")}
+        L, case = m["KG_train"].offline_generation(
+            grid, torch.full((n,), 1.0 / n), N, NI, NB, p["IC_u1"], p["IC_u2"], p["BC_u"], p["xcos"],
+            v["out"], v["out_xx"], v["out_tt"], v["out_IC"], v["out_IC_t"], v["out_BC"], p["f_hat"],
+            epochs, lr)
+        save[f"n{n}_c"] = C
+        save[f"n{n}_f"] = F
+        save[f"n{n}_m"] = M
+        save[f"n{n}_trace"] = T
+        save[f"n{n}_L"] = np.float32(float(L))
+        save[f"n{n}_case"] = np.array(case, np.float64)
+        print(tag, "n", n, "L", float(L), "case", case, flush=True)
+    if test_mu is not None:
+        n = nmax
+        c0 = torch.full((n,), 1.0 / n)
+        times, soln = m["KG_test"].gpt_test(
+            test_mu, p["out"], p["out_xx"], p["out_tt"], p["out_IC"], p["out_IC_t"], p["out_BC"],
+            p["f_hat"], p["xcos"], N, NI, NB, p["IC_u1"], p["IC_u2"], p["BC_u"], c0, test_epochs, lr,
+            p["out_test"])
+        losses = m["KG_test"].gpt_test_loss(
+            test_mu, p["out"], p["out_xx"], p["out_tt"], p["out_IC"], p["out_IC_t"], p["out_BC"],
+            p["f_hat"], p["xcos"], N, NI, NB, p["IC_u1"], p["IC_u2"], p["BC_u"], c0, test_epochs, lr)
+        save.update(test_mu=test_mu, test_epochs=test_epochs, test_soln=soln, test_losses=losses)
+    np.savez_compressed(os.path.join(OUT, tag + ".npz"), **save)
+    print("wrote", tag)
+
+
+def kg_grid(na, nb, ng):
+    a = np.linspace(-2, -1, na)
+    b = np.linspace(0, 1, nb)
+    g = np.linspace(0, 1, ng)
+    return np.array(np.meshgrid(a, b, g)).T.reshape(-1, 3)   # KG_main.py:46-49 ordering
+
+
+def gen_kg_small():
+    grid = kg_grid(4, 3, 5)
+    rng = np.random.default_rng(1234)
+    test_mu = grid[rng.choice(len(grid), 6, replace=False)]
+    kg_case("kg_small", 24, 64, 64, 10, [1, 2, 7, 15], grid, 300, 0.025, 50, test_mu, 1000)
+
+
+def gen_kg_nonmono():
+    """Large lr: non-monotone / diverging trajectories exercise the exact N1 arg-max scan."""
+    grid = kg_grid(3, 3, 4)
+    kg_case("kg_nonmono", 16, 32, 32, 8, [3, 6], grid, 120, {3: 0.28, 6: 0.13}, 20, None, 0, nmax=6)
+
+
+def gen_kg_full():
+    grid = kg_grid(10, 10, 10)
+    rng = np.random.default_rng(7)
+    sel = np.sort(rng.choice(len(grid), 10, replace=False))
+    kg_case("kg_full", 100, 512, 512, 40, [15], grid[sel], 2000, 0.025, 500, None, 0)
+
+
+GENS = {"kg_small": gen_kg_small, "kg_nonmono": gen_kg_nonmono, "kg_full": gen_kg_full}
+
+if __name__ == "__main__":
+    torch.set_num_threads(int(os.environ.get("OMP_NUM_THREADS", "8")))
+    which = sys.argv[1:] or ["all"]
+    os.makedirs(OUT, exist_ok=True)
+    for name, fn in GENS.items():
+        if "all" in which or name in which:
+            fn()
