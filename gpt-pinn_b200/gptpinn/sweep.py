@@ -49,19 +49,10 @@ def _vec(t, name, keep, rows):
     return t.data_ptr()
 
 
-_zero_cache = {}
-
-
 def _is_all_zero(t):
-    """One device->host sync per distinct tensor version (f_hat / IC_u2 are zero in every shipped problem)."""
-    key = (t.data_ptr(), t._version, tuple(t.shape))
-    hit = _zero_cache.get(key)
-    if hit is None:
-        if len(_zero_cache) > 64:
-            _zero_cache.clear()
-        hit = not bool(torch.any(t != 0).item())
-        _zero_cache[key] = hit
-    return hit
+    """f_hat / IC_u2 / BC_u are zero in every shipped problem; an all-zero target is passed as NULL so the
+    kernel skips it.  Costs one tiny reduction + host sync per call (not cached: addresses get reused)."""
+    return not bool(torch.any(t != 0).item())
 
 
 def _opt_vec(t, name, keep, rows):
