@@ -205,8 +205,12 @@ static int run_sweep(gptpinn_handle *h, int pde, int n, const Segments &seg, Pac
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev != h->device) return fail(GPTPINN_E_INVALID, "handle belongs to device %d, current device is %d", h->device, dev);
     if (a->epochs < 0) return fail(GPTPINN_E_INVALID, "epochs < 0");
-    if (!a->f_out_dev || !a->m_out_dev || !a->c0_dev) return fail(GPTPINN_E_INVALID, "f_out_dev, m_out_dev and c0_dev are required");
+    if (a->Np > 0 && (!a->f_out_dev || !a->m_out_dev || !a->c0_dev)) return fail(GPTPINN_E_INVALID, "f_out_dev, m_out_dev and c0_dev are required");
 
+    if (a->Np == 0) {
+        if (info) memset(info, 0, sizeof(*info));
+        return GPTPINN_OK;
+    }
     Plan plan;
     int rc = make_plan(rows, n, h->n_sm, seg.rows[0], a, plan);
     if (rc) return rc;
