@@ -15,7 +15,7 @@
 #include "sweep_kernel.cuh"
 
 namespace gp {
-#define GP_DECL(P, N) cudaError_t sweep_launch_##P##_##N(const SweepParams &, int, int, size_t, cudaStream_t);
+#define GP_DECL(P, N) cudaError_t sweep_launch_##P##_##N(const SweepParams &, int, int, int, size_t, cudaStream_t);
 #define GP_DECL_ALL(P) GP_DECL(P, 1) GP_DECL(P, 2) GP_DECL(P, 3) GP_DECL(P, 4) GP_DECL(P, 5) GP_DECL(P, 6) GP_DECL(P, 7) GP_DECL(P, 8) GP_DECL(P, 9)
 GP_DECL_ALL(0) GP_DECL_ALL(1) GP_DECL_ALL(2)
 GP_DECL(0, 10) GP_DECL(0, 11) GP_DECL(0, 12) GP_DECL(0, 13) GP_DECL(0, 14) GP_DECL(0, 15)
@@ -50,6 +50,7 @@ struct gptpinn_handle {
     float *packed = nullptr;   size_t packed_cap = 0;     // floats
     void *items = nullptr;     size_t items_cap = 0;      // bytes
     void *sibs = nullptr;      size_t sibs_cap = 0;       // bytes
+    unsigned int *counter = nullptr;                      // work-item ticket
 };
 
 static int ensure(void **ptr, size_t *cap, size_t need)
@@ -90,6 +91,7 @@ extern "C" int gptpinn_destroy(gptpinn_handle *h)
     if (h->packed) cudaFree(h->packed);
     if (h->items) cudaFree(h->items);
     if (h->sibs) cudaFree(h->sibs);
+    if (h->counter) cudaFree(h->counter);
     delete h;
     return GPTPINN_OK;
 }
@@ -108,25 +110,100 @@ static inline uint64_t key_of(const ParamRow &r)
 }
 
 struct Plan {
-    int M = 1, SL = 1, W = 1, ctas = 1, rounds = 1, groups = 0;
+    int M = 1, SL = 1, W = 1, ctas = 1, rounds = 1, groups = 0, priv = 0;
     std::vector<ItemDesc> items;
     std::vector<SibDesc> sibs;
 };
 
-static double model_cost(int n, int M, int SL, int W, long long items, int n_sm, int rounds, long long rows)
+// ---- cost model (warp-instruction counts; one SMSP issues one warp-instruction per cycle) ----
+static double per_row_instr(int pde, int n, int M)
+{
+    const double fma = (pde == PDE_B ? 6.0 : 4.0) * n;
+    return M * (fma + 8.0) + (pde == PDE_B ? 3.0 : 2.0) * ((n + 3) / 4) + 8.0;
+}
+static double item_instr(int pde, int n, int M, int SL, long long rows_total, long long tiles, int rt)
 {
     const int RL = 32 / SL;
-    const double rows_lane = (double)rows / RL;
-    const double per_row = M * (4.0 * n + 8.0) + 2.0 * ((n + 3) / 4) + 6.0;
-    const double build = (double)rows / R_TILE * 25.0 * (n / 4 + 1) * R_TILE / 32.0;
-    const double issue = std::ceil(W / 4.0) * (rows_lane * per_row + build);
-    const double wf = std::max(1.0, RL / 8.0);
-    const double smem = (double)W * rows_lane * 2.0 * ((n + 3) / 4) * wf;
-    (void)items; (void)n_sm;
-    return rounds * std::max(issue, smem);
+    const double rows_lane = (double)tiles * ((rt + RL - 1) / RL);     // every tile costs whole lane-rows
+    const double build = (double)tiles * (28.0 * (n / 4 + 1) * rt / 32.0 + 40.0);
+    (void)rows_total;
+    return rows_lane * per_row_instr(pde, n, M) + build;
+}
+static const double kL2BytesPerCycle = 4000.0;       // chip-wide L2 -> SM budget the planner allows itself
+
+// makespan of `t` (already in hand-out order) on `workers` identical workers, greedy (= ticket order)
+static double makespan(const std::vector<double> &t, int workers)
+{
+    if (t.empty()) return 0.0;
+    std::vector<double> heap((size_t)std::min<size_t>(workers, t.size()), 0.0);   // min-heap of finish times
+    auto cmp = [](double x, double y) { return x > y; };
+    double mx = 0.0;
+    for (double d : t) {
+        std::pop_heap(heap.begin(), heap.end(), cmp);
+        double f = heap.back() + d;
+        heap.back() = f;
+        std::push_heap(heap.begin(), heap.end(), cmp);
+        if (f > mx) mx = f;
+    }
+    return mx;
 }
 
-static int make_plan(std::vector<ParamRow> &rows, int n, int n_sm, long long data_rows,
+struct Chunk { int g, s0, cnt, SL; };     // siblings [s0, s0+cnt) of group g on SL sibling-lanes
+
+// binary decomposition of every group into power-of-two lane counts, largest first
+static void decompose(const std::vector<int> &gstart, int M, std::vector<Chunk> &out)
+{
+    out.clear();
+    const int ngroups = (int)gstart.size() - 1;
+    for (int g = 0; g < ngroups; ++g) {
+        int S = gstart[g + 1] - gstart[g], s0 = 0;
+        while (S > 0) {
+            int lanes = (S + M - 1) / M;                 // sibling lanes still needed
+            int SL = 32;
+            while (SL > lanes) SL >>= 1;                 // largest power of two <= lanes
+            if (SL < lanes && SL * 2 <= 32 && (long long)SL * 2 * M - S < M) SL *= 2;   // a last partial lane
+            const int cnt = std::min(S, SL * M);
+            out.push_back({g, s0, cnt, SL});
+            s0 += cnt; S -= cnt;
+        }
+    }
+    std::stable_sort(out.begin(), out.end(), [](const Chunk &x, const Chunk &y) { return x.SL > y.SL; });
+}
+
+// split the chunks of the last partial "round" so that the tail of the ticket queue is made of short items
+static void refine_tail(std::vector<Chunk> &ch, int M, int workers, int pde, int n, long long tiles, int rt)
+{
+    if (ch.empty()) return;
+    auto cost_of = [&](const std::vector<Chunk> &v) {
+        std::vector<double> t(v.size());
+        for (size_t i = 0; i < v.size(); ++i) t[i] = item_instr(pde, n, M, v[i].SL, 0, tiles, rt);
+        return makespan(t, workers);
+    };
+    double best = cost_of(ch);
+    for (int iter = 0; iter < 5; ++iter) {
+        const int bigSL = ch.front().SL;
+        if (bigSL <= 1) break;
+        size_t nbig = 0;
+        while (nbig < ch.size() && ch[nbig].SL == bigSL) ++nbig;
+        const size_t r = nbig % (size_t)workers;            // big items of the last partial round
+        if (r == 0) break;
+        std::vector<Chunk> v(ch.begin(), ch.begin() + (nbig - r));
+        std::vector<Chunk> rest(ch.begin() + nbig, ch.end());
+        for (size_t i = nbig - r; i < nbig; ++i) {           // halve
+            const Chunk &c = ch[i];
+            const int half = c.SL / 2, cap = half * M;
+            const int c1 = std::min(c.cnt, cap);
+            rest.push_back({c.g, c.s0, c1, half});
+            if (c.cnt > c1) rest.push_back({c.g, c.s0 + c1, c.cnt - c1, half});
+        }
+        std::stable_sort(rest.begin(), rest.end(), [](const Chunk &x, const Chunk &y) { return x.SL > y.SL; });
+        v.insert(v.end(), rest.begin(), rest.end());
+        const double cst = cost_of(v);
+        if (cst < best * 0.995) { best = cst; ch.swap(v); } else break;
+    }
+}
+
+static int make_plan(std::vector<ParamRow> &rows, int pde, int n, int n_sm, const long long *seg_rows, int nseg,
                      const gptpinn_sweep_args *a, Plan &plan)
 {
     std::stable_sort(rows.begin(), rows.end(), [](const ParamRow &x, const ParamRow &y) { return key_of(x) < key_of(y); });
@@ -136,59 +213,99 @@ static int make_plan(std::vector<ParamRow> &rows, int n, int n_sm, long long dat
     gstart.push_back((int)rows.size());
     plan.groups = (int)gstart.size() - 1;
 
-    auto count_items = [&](int M, int SL) {
-        long long it = 0;
-        for (int g = 0; g < plan.groups; ++g) { int S = gstart[g + 1] - gstart[g]; it += (S + M * SL - 1) / (M * SL); }
-        return it;
-    };
+    long long tiles_p = 0, tiles_s = 0;
+    for (int s = 0; s < nseg; ++s) { tiles_p += (seg_rows[s] + RT_PRIV - 1) / RT_PRIV; tiles_s += (seg_rows[s] + RT_SHARED - 1) / RT_SHARED; }
+    const double slot_p = (pde == PDE_KG ? SlotFloats<PDE_KG, RT_PRIV>::value : pde == PDE_B ? SlotFloats<PDE_B, RT_PRIV>::value : SlotFloats<PDE_AC, RT_PRIV>::value) * 4.0;
+    const double slot_s = (pde == PDE_KG ? SlotFloats<PDE_KG, RT_SHARED>::value : pde == PDE_B ? SlotFloats<PDE_B, RT_SHARED>::value : SlotFloats<PDE_AC, RT_SHARED>::value) * 4.0;
+
     static const int Ms[4] = {5, 4, 2, 1};
-    int bestM = 0, bestSL = 0, bestW = 0;
-    if (a->cfg_M > 0 && a->cfg_SL > 0) {
-        bestM = a->cfg_M; bestSL = a->cfg_SL;
-        if (!(bestM == 1 || bestM == 2 || bestM == 4 || bestM == 5)) return fail(GPTPINN_E_INVALID, "cfg_M must be 1, 2, 4 or 5");
-        if (bestSL < 1 || bestSL > 32 || (bestSL & (bestSL - 1))) return fail(GPTPINN_E_INVALID, "cfg_SL must be a power of two <= 32");
-        long long it = count_items(bestM, bestSL);
-        int maxw = maxw_for_m(bestM);
-        bestW = a->cfg_W > 0 ? std::min(a->cfg_W, maxw) : (int)std::min<long long>(maxw, (it + n_sm - 1) / n_sm);
-    } else {
-        double best = 1e300;
-        for (int mi = 0; mi < 4; ++mi)
+    const int mode = a->cfg_mode;                     // 0 auto, 1 shared ring, 2 private rings
+    if (a->cfg_M != 0 && !(a->cfg_M == 1 || a->cfg_M == 2 || a->cfg_M == 4 || a->cfg_M == 5))
+        return fail(GPTPINN_E_INVALID, "cfg_M must be 0, 1, 2, 4 or 5");
+    if (a->cfg_SL != 0 && (a->cfg_SL < 1 || a->cfg_SL > 32 || (a->cfg_SL & (a->cfg_SL - 1))))
+        return fail(GPTPINN_E_INVALID, "cfg_SL must be 0 or a power of two <= 32");
+    if (mode < 0 || mode > 2) return fail(GPTPINN_E_INVALID, "cfg_mode must be 0, 1 or 2");
+
+    double best = 1e300;
+    int bM = 0, bSL = 0, bW = 0, bPriv = 0;
+    std::vector<Chunk> bestChunks, ch;
+    for (int mi = 0; mi < 4; ++mi) {
+        const int M = Ms[mi];
+        if (a->cfg_M > 0 && M != a->cfg_M) continue;
+        const int maxw = maxw_for_m(M);
+        // ---- private rings: dynamic tickets, mixed item sizes ----
+        if (mode != 1) {
+            const int W = a->cfg_W > 0 ? std::min(a->cfg_W, maxw) : maxw;
+            const int workers = n_sm * W;
+            if (a->cfg_SL > 0) {
+                ch.clear();
+                for (int g = 0; g < plan.groups; ++g)
+                    for (int s0 = 0, S = gstart[g + 1] - gstart[g]; s0 < S; s0 += a->cfg_SL * M)
+                        ch.push_back({g, s0, std::min(S - s0, a->cfg_SL * M), a->cfg_SL});
+            } else {
+                decompose(gstart, M, ch);
+                refine_tail(ch, M, workers, pde, n, tiles_p, RT_PRIV);
+            }
+            std::vector<double> t(ch.size());
+            for (size_t i = 0; i < ch.size(); ++i) t[i] = item_instr(pde, n, M, ch[i].SL, 0, tiles_p, RT_PRIV);
+            const double wps = std::ceil(std::min<double>(W, (double)ch.size() / n_sm + 0.999) / 4.0);   // warps sharing an SMSP
+            const double issue = makespan(t, workers) * std::max(1.0, wps);
+            const double l2 = (double)ch.size() * tiles_p * slot_p / kL2BytesPerCycle;
+            const double cst = std::max(issue, l2);
+            if (cst < best) { best = cst; bM = M; bSL = ch.empty() ? 1 : ch.front().SL; bW = W; bPriv = 1; bestChunks = ch; }
+        }
+        // ---- shared ring: static rounds, uniform item size ----
+        if (mode != 2) {
             for (int SL = 1; SL <= 32; SL <<= 1) {
-                const int M = Ms[mi];
-                const long long it = count_items(M, SL);
-                const int maxw = maxw_for_m(M);
+                if (a->cfg_SL > 0 && SL != a->cfg_SL) continue;
+                long long nit = 0;
+                for (int g = 0; g < plan.groups; ++g) { const int S = gstart[g + 1] - gstart[g]; nit += (S + M * SL - 1) / (M * SL); }
                 for (int W = 1; W <= maxw; ++W) {
                     if (a->cfg_W > 0 && W != std::min(a->cfg_W, maxw)) continue;
-                    const long long ctas = std::min<long long>(n_sm, (it + W - 1) / W);
-                    const int rounds = (int)((it + ctas * W - 1) / (ctas * W));
-                    const double cst = model_cost(n, M, SL, W, it, n_sm, rounds, data_rows);
-                    if (cst < best) { best = cst; bestM = M; bestSL = SL; bestW = W; }
+                    const long long ctas = std::min<long long>(n_sm, (nit + W - 1) / W);
+                    const double rounds = (double)((nit + ctas * W - 1) / (ctas * W));
+                    const double issue = rounds * std::ceil(W / 4.0) * item_instr(pde, n, M, SL, 0, tiles_s, RT_SHARED);
+                    const double l2 = rounds * ctas * tiles_s * slot_s / kL2BytesPerCycle;
+                    const double cst = std::max(issue, l2) * 1.02;          // ties go to the private rings
+                    if (cst < best) { best = cst; bM = M; bSL = SL; bW = W; bPriv = 0; }
                 }
             }
-    }
-    plan.M = bestM; plan.SL = bestSL; plan.W = std::max(1, bestW);
-    const int cap = plan.M * plan.SL;
-    plan.items.clear(); plan.sibs.clear();
-    plan.sibs.reserve(rows.size());
-    for (int g = 0; g < plan.groups; ++g) {
-        for (int s0 = gstart[g]; s0 < gstart[g + 1]; s0 += cap) {
-            ItemDesc it;
-            memset(&it, 0, sizeof(it));
-            it.tp0 = rows[s0].tp0; it.tp1 = rows[s0].tp1;
-            it.sib_start = (int)plan.sibs.size();
-            it.sib_count = std::min(cap, gstart[g + 1] - s0);
-            it.SL = plan.SL;
-            for (int s = 0; s < it.sib_count; ++s) {
-                SibDesc sd;
-                sd.sp0 = rows[s0 + s].sp0; sd.sp1 = rows[s0 + s].sp1; sd.out_idx = rows[s0 + s].idx; sd.pad = 0;
-                plan.sibs.push_back(sd);
-            }
-            plan.items.push_back(it);
         }
     }
+    if (bM == 0) return fail(GPTPINN_E_INVALID, "no feasible sweep configuration");
+    plan.M = bM; plan.SL = bSL; plan.W = std::max(1, bW); plan.priv = bPriv;
+    if (!bPriv) {
+        bestChunks.clear();
+        for (int g = 0; g < plan.groups; ++g)
+            for (int s0 = 0, S = gstart[g + 1] - gstart[g]; s0 < S; s0 += bSL * bM)
+                bestChunks.push_back({g, s0, std::min(S - s0, bSL * bM), bSL});
+    }
+    plan.items.clear(); plan.sibs.clear();
+    plan.sibs.reserve(rows.size());
+    plan.items.reserve(bestChunks.size());
+    for (const Chunk &c : bestChunks) {
+        const int base = gstart[c.g] + c.s0;
+        ItemDesc it;
+        memset(&it, 0, sizeof(it));
+        it.tp0 = rows[base].tp0; it.tp1 = rows[base].tp1;
+        it.sib_start = (int)plan.sibs.size();
+        it.sib_count = c.cnt;
+        it.SL = c.SL;
+        for (int s = 0; s < c.cnt; ++s) {
+            SibDesc sd;
+            sd.sp0 = rows[base + s].sp0; sd.sp1 = rows[base + s].sp1; sd.out_idx = rows[base + s].idx; sd.pad = 0;
+            plan.sibs.push_back(sd);
+        }
+        plan.items.push_back(it);
+    }
     const long long nit = (long long)plan.items.size();
-    plan.ctas = (int)std::min<long long>(n_sm, (nit + plan.W - 1) / plan.W);
-    plan.rounds = (int)((nit + (long long)plan.ctas * plan.W - 1) / ((long long)plan.ctas * plan.W));
+    if (bPriv) {
+        plan.ctas = (int)std::min<long long>(n_sm, (nit + plan.W - 1) / plan.W);
+        plan.rounds = (int)((nit + (long long)plan.ctas * plan.W - 1) / ((long long)plan.ctas * plan.W));
+    } else {
+        plan.ctas = (int)std::min<long long>(n_sm, (nit + plan.W - 1) / plan.W);
+        plan.rounds = (int)((nit + (long long)plan.ctas * plan.W - 1) / ((long long)plan.ctas * plan.W));
+    }
     return GPTPINN_OK;
 }
 
@@ -212,25 +329,28 @@ static int run_sweep(gptpinn_handle *h, int pde, int n, const Segments &seg, Pac
         return GPTPINN_OK;
     }
     Plan plan;
-    int rc = make_plan(rows, n, h->n_sm, seg.rows[0], a, plan);
+    int rc = make_plan(rows, pde, n, h->n_sm, seg.rows, seg.nseg, a, plan);
     if (rc) return rc;
 
-    const int slot = pde == PDE_KG ? SlotFloats<PDE_KG>::value : (pde == PDE_B ? SlotFloats<PDE_B>::value : SlotFloats<PDE_AC>::value);
+    const int RT = plan.priv ? RT_PRIV : RT_SHARED;
+    const int slot = plan.priv ? (pde == PDE_KG ? SlotFloats<PDE_KG, RT_PRIV>::value : (pde == PDE_B ? SlotFloats<PDE_B, RT_PRIV>::value : SlotFloats<PDE_AC, RT_PRIV>::value))
+                               : (pde == PDE_KG ? SlotFloats<PDE_KG, RT_SHARED>::value : (pde == PDE_B ? SlotFloats<PDE_B, RT_SHARED>::value : SlotFloats<PDE_AC, RT_SHARED>::value));
     SweepParams p;
     memset(&p, 0, sizeof(p));
     long long tiles = 0, max_rows = 0;
     long long tile0[MAX_SEG];
     for (int s = 0; s < seg.nseg; ++s) {
         tile0[s] = tiles;
-        p.ntile[s] = (int)((seg.rows[s] + R_TILE - 1) / R_TILE);
+        p.ntile[s] = (int)((seg.rows[s] + RT - 1) / RT);
         tiles += p.ntile[s];
         max_rows = std::max(max_rows, seg.rows[s]);
     }
     for (int i = 0; i < jobs.nmat; ++i) jobs.mat[i].tile0 = tile0[jobs.mat[i].tile0];
     for (int i = 0; i < jobs.nvec; ++i) jobs.vec[i].tile0 = tile0[jobs.vec[i].tile0];
     jobs.slot = slot;
+    jobs.rt = RT;
     const unsigned long long total_tiles = (unsigned long long)plan.rounds * (unsigned long long)(a->epochs + 1) * (unsigned long long)tiles;
-    if (total_tiles >= 0xfffffff0ull) return fail(GPTPINN_E_UNSUPPORTED, "rounds*epochs*tiles = %llu overflows the tile counter", total_tiles);
+    if (!plan.priv && total_tiles >= 0xfffffff0ull) return fail(GPTPINN_E_UNSUPPORTED, "rounds*epochs*tiles = %llu overflows the tile counter", total_tiles);
 
     size_t cap_f = h->packed_cap * sizeof(float);
     rc = ensure((void **)&h->packed, &cap_f, (size_t)tiles * slot * sizeof(float));
@@ -241,6 +361,8 @@ static int run_sweep(gptpinn_handle *h, int pde, int n, const Segments &seg, Pac
     rc = ensure(&h->sibs, &h->sibs_cap, plan.sibs.size() * sizeof(SibDesc));
     if (rc) return rc;
 
+    if (!h->counter) CUDA_TRY(cudaMalloc((void **)&h->counter, sizeof(unsigned int)));
+    CUDA_TRY(cudaMemsetAsync(h->counter, 0, sizeof(unsigned int), st));
     CUDA_TRY(cudaMemsetAsync(h->packed, 0, (size_t)tiles * slot * sizeof(float), st));
     CUDA_TRY(launch_pack(jobs, h->packed, max_rows, st));
     CUDA_TRY(cudaMemcpyAsync(h->items, plan.items.data(), plan.items.size() * sizeof(ItemDesc), cudaMemcpyHostToDevice, st));
@@ -265,15 +387,19 @@ static int run_sweep(gptpinn_handle *h, int pde, int n, const Segments &seg, Pac
     p.trace = p.rec_every > 0 ? a->trace_dev : nullptr;
     p.W = plan.W;
     p.rounds = plan.rounds;
+    p.counter = h->counter;
 
     const int NQT = n / 4 + 1;
-    const size_t smem = (size_t)NSTAGE * slot * 4 + (size_t)plan.W * NQT * QSTRIDE * 4 + 2 * NSTAGE * sizeof(uint64_t);
+    const size_t smem = plan.priv
+        ? (size_t)plan.W * NST_PRIV * slot * 4 + (size_t)plan.W * NQT * 4 * RT * 4 + (size_t)plan.W * NST_PRIV * sizeof(uint64_t)
+        : (size_t)NSTAGE * slot * 4 + (size_t)plan.W * NQT * 4 * RT * 4 + 2 * NSTAGE * sizeof(uint64_t);
+    if (smem > 227 * 1024) return fail(GPTPINN_E_UNSUPPORTED, "configuration needs %zu bytes of shared memory", smem);
     sweep_launch_fn fn = kLaunch[pde][n - 1];
     if (!fn) return fail(GPTPINN_E_UNSUPPORTED, "no kernel compiled for pde=%d n=%d", pde, n);
-    if (p.n_items > 0) CUDA_TRY(fn(p, plan.M, plan.ctas, smem, st));
+    if (p.n_items > 0) CUDA_TRY(fn(p, plan.M, plan.priv, plan.ctas, smem, st));
     if (info) {
         info->M = plan.M; info->SL = plan.SL; info->W = plan.W; info->items = p.n_items; info->groups = plan.groups;
-        info->ctas = plan.ctas; info->rounds = plan.rounds; info->kernels_launched = p.n_items > 0 ? 2 : 1;
+        info->ctas = plan.ctas; info->rounds = plan.rounds; info->priv = plan.priv; info->kernels_launched = p.n_items > 0 ? 2 : 1;
         info->smem_bytes = (int)smem; info->tiles_per_pass = (int)tiles;
     }
     return GPTPINN_OK;

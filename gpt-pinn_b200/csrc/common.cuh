@@ -14,19 +14,22 @@ namespace gp {
 //
 //   stream = tile[0] tile[1] ... tile[tiles_per_pass-1]        (segment after segment)
 //   tile   = NARR matrix blocks, then NVEC row vectors          (SLOT floats, 16-B multiple)
-//   matrix block = [4 column-quads][R_TILE rows][4 floats]      (k = 4*quad + lane component)
-//   row vector   = [R_TILE]
+//   matrix block = [4 column-quads][RT rows][4 floats]          (k = 4*quad + lane component)
+//   row vector   = [RT]                                          (RT = rows per tile, 32 or 64)
 //
 // so that (a) one tile is ONE contiguous cp.async.bulk (TMA bulk copy) into shared memory,
 // (b) a thread reads 4 neurons of one row with one LDS.128, and (c) the row-slices of a warp
 // touch consecutive 16-B chunks (bank-conflict free), while lanes that share a row broadcast.
 // Rows past N and columns past n are zero, which contributes nothing to any sum.
 // ----------------------------------------------------------------------------------------
-constexpr int R_TILE   = 64;                 // rows per tile
-constexpr int QSTRIDE  = R_TILE * 4;         // floats in one column-quad plane
-constexpr int ARR_FLTS = 4 * QSTRIDE;        // one matrix block (16 columns)
-constexpr int NSTAGE   = 4;                  // shared-memory ring depth
-constexpr int LOOKAHEAD = 2;                 // tiles in flight ahead of the consumers
+// Two tile heights are compiled: RT = 32 for the "private ring" kernels (every warp streams its
+// own copy of the tiles: no inter-warp coupling, dynamic work distribution) and RT = 64 for the
+// "shared ring" kernels (all warps of a CTA consume one stream: small grids, rows split 32 ways).
+constexpr int RT_PRIV   = 32;
+constexpr int RT_SHARED = 64;
+constexpr int NSTAGE   = 4;                  // shared ring depth
+constexpr int LOOKAHEAD = 2;                 // shared ring: tiles in flight ahead of the consumers
+constexpr int NST_PRIV = 3;                  // private ring depth (per warp)
 constexpr int MAX_SEG  = 4;
 
 constexpr int PDE_KG = 0, PDE_B = 1, PDE_AC = 2;
@@ -41,7 +44,7 @@ template <> struct PdeTraits<PDE_B> {       // residual: Pt,Pxx,Px,P | fhat ; IC
 template <> struct PdeTraits<PDE_AC> {      // residual: Pt,Pxx,P | fhat ; IC: PIC | ICu ; BC: Pub,Plb,Pdiff ; BCx: Pubx,Plbx,Pdiffx
     static constexpr int NARR = 3, NVEC = 1, NSEG = 4, TARR = 1;
 };
-template <int PDE> struct SlotFloats { static constexpr int value = PdeTraits<PDE>::NARR * ARR_FLTS + PdeTraits<PDE>::NVEC * R_TILE; };
+template <int PDE, int RT> struct SlotFloats { static constexpr int value = PdeTraits<PDE>::NARR * 16 * RT + PdeTraits<PDE>::NVEC * RT; };
 
 struct ItemDesc {          // one warp work item: a set of parameters that share the same T
     float tp0, tp1;        // KG: alpha, beta    B: -nu, 0      AC: -lambda, -eps
@@ -72,9 +75,14 @@ struct SweepParams {
     int            c0_per_param;
     float          *c_out, *f_out, *m_out, *trace;
     int            W;                // warps per CTA
-    int            rounds;
+    int            rounds;           // shared-ring kernels: static rounds of gridDim.x * W items
+    unsigned int  *counter;          // private-ring kernels: global work-item ticket (zeroed before launch)
 };
 
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 // ---- PTX wrappers: mbarrier + TMA bulk copy --------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

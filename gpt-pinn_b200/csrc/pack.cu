@@ -15,16 +15,16 @@ __global__ void pack_kernel(const PackJobs jobs, float *__restrict__ stream)
         const int k = (int)(e & 15);
         if (row >= m.nrows || k >= m.ncols) return;
         const float v = m.src[row * m.ld + k];
-        const long long tile = m.tile0 + row / R_TILE;
-        const int r = (int)(row % R_TILE);
-        stream[tile * jobs.slot + (long long)m.arr * ARR_FLTS + (k >> 2) * QSTRIDE + r * 4 + (k & 3)] = v;
+        const long long tile = m.tile0 + row / jobs.rt;
+        const int r = (int)(row % jobs.rt);
+        stream[tile * jobs.slot + (long long)m.arr * 16 * jobs.rt + (k >> 2) * 4 * jobs.rt + r * 4 + (k & 3)] = v;
     } else {
         const PackVec &v = jobs.vec[j - jobs.nmat];
         const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
         if (row >= v.nrows || v.src == nullptr) return;
-        const long long tile = v.tile0 + row / R_TILE;
-        const int r = (int)(row % R_TILE);
-        stream[tile * jobs.slot + (long long)jobs.narr * ARR_FLTS + v.vec * R_TILE + r] = v.src[row];
+        const long long tile = v.tile0 + row / jobs.rt;
+        const int r = (int)(row % jobs.rt);
+        stream[tile * jobs.slot + (long long)jobs.narr * 16 * jobs.rt + v.vec * jobs.rt + r] = v.src[row];
     }
 }
 

@@ -23,6 +23,7 @@ struct PackJobs {
     PackVec vec[8];
     int     nmat, nvec;
     int     narr;          // matrix blocks per slot
+    int     rt;            // rows per tile
     long long slot;        // floats per slot
 };
 

@@ -5,8 +5,8 @@
 #define GP_CAT(a, b, c) GP_CAT2(a, b, c)
 
 namespace gp {
-cudaError_t GP_CAT(sweep_launch_, GP_PDE, GP_N)(const SweepParams &p, int M, int ctas, size_t smem, cudaStream_t st)
+cudaError_t GP_CAT(sweep_launch_, GP_PDE, GP_N)(const SweepParams &p, int M, int priv, int ctas, size_t smem, cudaStream_t st)
 {
-    return launch_n<GP_PDE, GP_N>(p, M, ctas, smem, st);
+    return launch_n<GP_PDE, GP_N>(p, M, priv, ctas, smem, st);
 }
 }  // namespace gp

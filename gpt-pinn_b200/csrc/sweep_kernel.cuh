@@ -9,14 +9,20 @@
 //           T (KG: same (alpha,beta); their gammas differ).  Lanes = SL sibling-lanes x RL
 //           row-slices (SL*RL = 32); each thread owns M parameters: c[M][N], grad[M][N] and
 //           the loss sums live in registers for the whole run.
-//   CTA   = W warps that consume the same tile stream: a 4-deep shared-memory ring filled by
-//           TMA bulk copies (cp.async.bulk + mbarrier complete_tx), full/empty mbarriers.
-//   T     = per-warp [NQT][R_TILE][4] block in shared memory, rebuilt from the staged
-//           P-derivative tiles for every residual tile (2 FMA/element amortised over the
-//           siblings) so the inner loop spends the reference's 4n FMA per row and parameter.
+//   tiles = the packed activation stream (common.cuh) enters shared memory by TMA bulk copies
+//           (cp.async.bulk + mbarrier complete_tx).  Two pipeline flavours:
+//             PRIV = true : every warp owns a 3-deep ring of 32-row tiles and pulls work items
+//                           from a global ticket -- no inter-warp coupling at all (large grids);
+//             PRIV = false: the W warps of a CTA share a 4-deep ring of 64-row tiles with
+//                           full/empty mbarriers and static rounds (small grids, RL = 32).
+//   T     = per-warp [NQT][RT][4] block in shared memory, rebuilt from the staged P-derivative
+//           tiles for every residual tile (2 FMA/element amortised over the siblings) so the
+//           inner loop spends the reference's 4n FMA per row and parameter.
 //   epoch = one pass over the tile stream (all residual, IC, BC tiles); at its end the RL
 //           row-slices are summed with xor-shuffles (fixed order => bitwise deterministic),
 //           the loss of the *current* c falls out of the same pass, then c <- c - lr*grad.
+//   inner loop: operands of the NEXT row are re-loaded quad by quad while the gradient FMAs of
+//           the current row retire (software pipelining; no extra registers).
 #pragma once
 #include "common.cuh"
 
@@ -25,14 +31,17 @@ namespace gp {
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 
-template <int NQX>
+template <int RT>
+__device__ __forceinline__ void load_quad(const float *blk, int r, int q, float *v)
+{
+    const float4 x = ld4(blk + q * (4 * RT) + r * 4);
+    v[4 * q + 0] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+}
+template <int NQX, int RT>
 __device__ __forceinline__ void load_row(const float *blk, int r, float (&v)[4 * NQX])
 {
 #pragma unroll
-    for (int q = 0; q < NQX; ++q) {
-        const float4 x = ld4(blk + q * QSTRIDE + r * 4);
-        v[4 * q + 0] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
-    }
+    for (int q = 0; q < NQX; ++q) load_quad<RT>(blk, r, q, v);
 }
 
 template <int N>
@@ -49,63 +58,100 @@ __device__ __forceinline__ void set_comp(float4 &t, int i, float v)
     if (i == 0) t.x = v; else if (i == 1) t.y = v; else if (i == 2) t.z = v; else t.w = v;
 }
 
-template <int PDE, int N, int M, int MAXW>
+template <int PDE, int N, int M, int MAXW, bool PRIV>
 __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p)
 {
     using TR = PdeTraits<PDE>;
+    constexpr int RT = PRIV ? RT_PRIV : RT_SHARED;
+    constexpr int QS = 4 * RT;               // floats per column-quad plane
+    constexpr int ARR = 16 * RT;             // floats per matrix block
     constexpr int NQ = (N + 3) / 4;          // column quads of a P block that hold data
     constexpr int NQT = N / 4 + 1;           // quads of T: N columns + the forcing column
-    constexpr int SLOT = SlotFloats<PDE>::value;
-    constexpr int TT = NQT * QSTRIDE;
-    constexpr int VEC0 = TR::NARR * ARR_FLTS, VEC1 = VEC0 + R_TILE;
+    constexpr int SLOT = SlotFloats<PDE, RT>::value;
+    constexpr int TT = NQT * QS;
+    constexpr int VEC0 = TR::NARR * ARR, VEC1 = VEC0 + RT;
+    constexpr int NST = PRIV ? NST_PRIV : NSTAGE;
     constexpr unsigned FULLM = 0xffffffffu;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *stage = reinterpret_cast<float *>(smem_raw);
-    float *Tall = stage + NSTAGE * SLOT;
-    uint64_t *full = reinterpret_cast<uint64_t *>(Tall + p.W * TT);
-    uint64_t *empty = full + NSTAGE;
-
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // PRIV  : [W][NST][SLOT] rings | [W][TT] T blocks | full[W][NST]
+    // shared: [NST][SLOT] ring     | [W][TT] T blocks | full[NST] empty[NST]
+    float *smem_f = reinterpret_cast<float *>(smem_raw);
+    float *ring = PRIV ? smem_f + (size_t)warp * NST * SLOT : smem_f;
+    float *Tall = smem_f + (size_t)(PRIV ? p.W : 1) * NST * SLOT;
     float *Tw = Tall + warp * TT;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(Tall + p.W * TT);
+    uint64_t *full = PRIV ? bars + warp * NST : bars;
+    uint64_t *empty = bars + NST;            // shared mode only
+
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], p.W); }
+        if (PRIV) {
+            for (int s = 0; s < p.W * NST; ++s) mbar_init(&bars[s], 1);
+        } else {
+            for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], p.W); }
+        }
         mbar_fence_init();
     }
     __syncthreads();
 
     const uint32_t tiles_pp = (uint32_t)p.tiles_per_pass;
-    const uint32_t total = (uint32_t)p.rounds * (uint32_t)(p.epochs + 1) * tiles_pp;
-    const bool producer = (threadIdx.x == 0);
     uint32_t gt = 0;                         // tiles consumed so far by this warp
+    // ---- shared ring state ----
+    const uint32_t total = PRIV ? 0u : (uint32_t)p.rounds * (uint32_t)(p.epochs + 1) * tiles_pp;
+    const bool producer = PRIV ? (lane == 0) : (threadIdx.x == 0);
+    // ---- private ring state ----
+    uint32_t next_tile = 0;                  // stream position of the next tile to issue (lane 0)
 
-    auto issue = [&](uint32_t lt) {
-        const uint32_t s = lt % NSTAGE, use = lt / NSTAGE;
+    auto issue_shared = [&](uint32_t lt) {
+        const uint32_t s = lt % NST, use = lt / NST;
         if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
         mbar_arrive_expect_tx(&full[s], SLOT * 4);
-        bulk_g2s(stage + s * SLOT, p.packed + (size_t)(lt % tiles_pp) * SLOT, SLOT * 4, &full[s]);
+        bulk_g2s(ring + s * SLOT, p.packed + (size_t)(lt % tiles_pp) * SLOT, SLOT * 4, &full[s]);
     };
-    if (producer)
-        for (uint32_t lt = 0; lt < (uint32_t)LOOKAHEAD && lt < total; ++lt) issue(lt);
+    auto issue_priv = [&](uint32_t s) {
+        mbar_arrive_expect_tx(&full[s], SLOT * 4);
+        bulk_g2s(ring + s * SLOT, p.packed + (size_t)next_tile * SLOT, SLOT * 4, &full[s]);
+        next_tile = (next_tile + 1 == tiles_pp) ? 0u : next_tile + 1;
+    };
+    if (producer) {
+        if (PRIV) { for (uint32_t s = 0; s < (uint32_t)NST; ++s) issue_priv(s); }
+        else { for (uint32_t lt = 0; lt < (uint32_t)LOOKAHEAD && lt < total; ++lt) issue_shared(lt); }
+    }
 
     auto acquire = [&]() -> const float * {
-        if (producer) { const uint32_t lt = gt + LOOKAHEAD; if (lt < total) issue(lt); }
-        __syncwarp();
-        const uint32_t s = gt % NSTAGE;
-        mbar_wait(&full[s], (gt / NSTAGE) & 1);
-        return stage + s * SLOT;
+        if (!PRIV) {
+            if (producer) { const uint32_t lt = gt + LOOKAHEAD; if (lt < total) issue_shared(lt); }
+            __syncwarp();
+        }
+        const uint32_t s = gt % NST;
+        mbar_wait(&full[s], (gt / NST) & 1);
+        return ring + s * SLOT;
     };
     auto release = [&]() {
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[gt % NSTAGE]);
+        if (PRIV) {
+            if (lane == 0) { fence_proxy_async(); issue_priv(gt % NST); }
+        } else {
+            if (lane == 0) mbar_arrive(&empty[gt % NST]);
+        }
         ++gt;
     };
 
     const float fac1 = p.fac1, fac2 = p.fac2, fac3 = p.fac3;
     const bool has_fhat = p.has_fhat != 0;
 
-    for (int round = 0; round < p.rounds; ++round) {
-        const int item = round * (int)gridDim.x * p.W + warp * (int)gridDim.x + (int)blockIdx.x;
+    for (int round = 0;; ++round) {
+        int item;
+        if (PRIV) {
+            int tk = 0;
+            if (lane == 0) tk = (int)atomicAdd(p.counter, 1u);
+            item = __shfl_sync(FULLM, tk, 0);
+            if (item >= p.n_items) break;
+        } else {
+            if (round >= p.rounds) break;
+            item = round * (int)gridDim.x * p.W + warp * (int)gridDim.x + (int)blockIdx.x;
+        }
         const bool active = item < p.n_items;
         ItemDesc it;
         it.tp0 = 0.f; it.tp1 = 0.f; it.sib_start = 0; it.sib_count = 0; it.SL = 32;
@@ -146,24 +192,18 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                 const float *slot = acquire();
                 if (active) {
                     // ---- per-warp T block (bit-identical to the reference's T tensor) -----
-                    for (int e = lane; e < NQT * R_TILE; e += 32) {
-                        const int q = e / R_TILE, r = e % R_TILE;
-                        const int o = q * QSTRIDE + r * 4;
+                    for (int e = lane; e < NQT * RT; e += 32) {
+                        const int q = e / RT, r = e % RT;
+                        const int o = q * QS + r * 4;
                         float4 tv;
-                        if constexpr (PDE == PDE_KG) {          // (Ptt + a*Pxx) + b*P   KG_precomp.py:23-26
-                            const float4 a = ld4(slot + o), b = ld4(slot + ARR_FLTS + o), d = ld4(slot + 2 * ARR_FLTS + o);
-                            tv.x = __fadd_rn(__fadd_rn(a.x, __fmul_rn(it.tp0, b.x)), __fmul_rn(it.tp1, d.x));
-                            tv.y = __fadd_rn(__fadd_rn(a.y, __fmul_rn(it.tp0, b.y)), __fmul_rn(it.tp1, d.y));
-                            tv.z = __fadd_rn(__fadd_rn(a.z, __fmul_rn(it.tp0, b.z)), __fmul_rn(it.tp1, d.z));
-                            tv.w = __fadd_rn(__fadd_rn(a.w, __fmul_rn(it.tp0, b.w)), __fmul_rn(it.tp1, d.w));
-                        } else if constexpr (PDE == PDE_B) {    // (-nu)*Pxx + Pt        B_precomp.py:18-20
-                            const float4 a = ld4(slot + o), b = ld4(slot + ARR_FLTS + o);
+                        if constexpr (PDE == PDE_B) {           // (-nu)*Pxx + Pt        B_precomp.py:18-20
+                            const float4 a = ld4(slot + o), b = ld4(slot + ARR + o);
                             tv.x = __fadd_rn(__fmul_rn(it.tp0, b.x), a.x);
                             tv.y = __fadd_rn(__fmul_rn(it.tp0, b.y), a.y);
                             tv.z = __fadd_rn(__fmul_rn(it.tp0, b.z), a.z);
                             tv.w = __fadd_rn(__fmul_rn(it.tp0, b.w), a.w);
-                        } else {                                // (Pt + (-l)*Pxx) + (-e)*P  AC_precompute.py:20-24
-                            const float4 a = ld4(slot + o), b = ld4(slot + ARR_FLTS + o), d = ld4(slot + 2 * ARR_FLTS + o);
+                        } else {    // KG: (Ptt + a*Pxx) + b*P  KG_precomp.py:23-26 ; AC: (Pt + (-l)*Pxx) + (-e)*P  AC_precompute.py:20-24
+                            const float4 a = ld4(slot + o), b = ld4(slot + ARR + o), d = ld4(slot + 2 * ARR + o);
                             tv.x = __fadd_rn(__fadd_rn(a.x, __fmul_rn(it.tp0, b.x)), __fmul_rn(it.tp1, d.x));
                             tv.y = __fadd_rn(__fadd_rn(a.y, __fmul_rn(it.tp0, b.y)), __fmul_rn(it.tp1, d.y));
                             tv.z = __fadd_rn(__fadd_rn(a.z, __fmul_rn(it.tp0, b.z)), __fmul_rn(it.tp1, d.z));
@@ -183,33 +223,21 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                     }
                     __syncwarp();
 
-                    for (int r = slice; r < R_TILE; r += RL) {
-                        float Tv[4 * NQT], Pv[4 * NQ];
-                        load_row<NQT>(Tw, r, Tv);
-                        float fh = 0.f;
-                        if constexpr (PDE == PDE_KG) {
-                            load_row<NQ>(slot + 2 * ARR_FLTS, r, Pv);
-                            if (has_fhat) fh = slot[VEC1 + r];
-#pragma unroll
-                            for (int m = 0; m < M; ++m) {
-                                const float u = dotn<N>(Pv, c[m], 0.f);
-                                const float t1 = dotn<N>(Tv, c[m], Tv[N]);
-                                const float d = fmaf(sp0[m], u * u, t1);       // residual - fhat
-                                lA[m] = fmaf(d, d, lA[m]);
-                                float first = d;
-                                if (has_fhat) first = d + fh;                    // update ignores fhat (N3)
-                                const float w2 = first * (sp1[m] * u);
-#pragma unroll
-                                for (int k = 0; k < N; ++k) {
-                                    g[m][k] = fmaf(first, Tv[k], g[m][k]);
-                                    g[m][k] = fmaf(w2, Pv[k], g[m][k]);
-                                }
-                            }
-                        } else if constexpr (PDE == PDE_B) {
-                            float Xv[4 * NQ];
-                            load_row<NQ>(slot + 2 * ARR_FLTS, r, Xv);
-                            load_row<NQ>(slot + 3 * ARR_FLTS, r, Pv);
-                            if (has_fhat) fh = slot[VEC0 + r];
+                    const float *Pblk = slot + (PDE == PDE_B ? 3 : 2) * ARR;
+                    const int fhoff = (PDE == PDE_KG) ? VEC1 : VEC0;
+                    int r = slice;
+                    float Tv[4 * NQT], Pv[4 * NQ];
+                    load_row<NQT, RT>(Tw, r, Tv);
+                    load_row<NQ, RT>(Pblk, r, Pv);
+                    float fh = 0.f;
+                    if (has_fhat) fh = slot[fhoff + r];
+                    if constexpr (PDE == PDE_B) {
+                        const float *Xblk = slot + 2 * ARR;
+                        float Xv[4 * NQ];
+                        load_row<NQ, RT>(Xblk, r, Xv);
+                        for (; r < RT; r += RL) {
+                            const int rn = min(r + RL, RT - 1);
+                            float first[M], wx[M], wp[M];
 #pragma unroll
                             for (int m = 0; m < M; ++m) {
                                 const float u = dotn<N>(Pv, c[m], 0.f);
@@ -217,34 +245,57 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                                 const float t1 = dotn<N>(Tv, c[m], Tv[N]);
                                 const float d = fmaf(u, ux, t1);
                                 lA[m] = fmaf(d, d, lA[m]);
-                                float first = d;
-                                if (has_fhat) first = d + fh;
-                                const float wx = first * u, wp = first * ux;
-#pragma unroll
-                                for (int k = 0; k < N; ++k) {
-                                    g[m][k] = fmaf(first, Tv[k], g[m][k]);
-                                    g[m][k] = fmaf(wx, Xv[k], g[m][k]);
-                                    g[m][k] = fmaf(wp, Pv[k], g[m][k]);
-                                }
+                                first[m] = has_fhat ? d + fh : d;
+                                wx[m] = first[m] * u; wp[m] = first[m] * ux;
                             }
-                        } else {
-                            load_row<NQ>(slot + 2 * ARR_FLTS, r, Pv);
-                            if (has_fhat) fh = slot[VEC0 + r];
+                            if (has_fhat) fh = slot[fhoff + rn];
+#pragma unroll
+                            for (int q = 0; q < NQT; ++q) {
+#pragma unroll
+                                for (int m = 0; m < M; ++m)
+#pragma unroll
+                                    for (int kk = 0; kk < 4; ++kk) {
+                                        const int k = 4 * q + kk;
+                                        if (k < N) {
+                                            g[m][k] = fmaf(first[m], Tv[k], g[m][k]);
+                                            g[m][k] = fmaf(wx[m], Xv[k], g[m][k]);
+                                            g[m][k] = fmaf(wp[m], Pv[k], g[m][k]);
+                                        }
+                                    }
+                                load_quad<RT>(Tw, rn, q, Tv);
+                                if (q < NQ) { load_quad<RT>(Pblk, rn, q, Pv); load_quad<RT>(Xblk, rn, q, Xv); }
+                            }
+                        }
+                    } else {
+                        for (; r < RT; r += RL) {
+                            const int rn = min(r + RL, RT - 1);
+                            float first[M], w2[M];
 #pragma unroll
                             for (int m = 0; m < M; ++m) {
                                 const float u = dotn<N>(Pv, c[m], 0.f);
                                 const float t1 = dotn<N>(Tv, c[m], Tv[N]);
-                                const float u2 = u * u;
-                                const float d = fmaf(sp0[m], u2 * u, t1);
+                                float d, nl;
+                                if constexpr (PDE == PDE_KG) { d = fmaf(sp0[m], u * u, t1); nl = sp1[m] * u; }          // g*u^2 ; 2g*u
+                                else { const float u2 = u * u; d = fmaf(sp0[m], u2 * u, t1); nl = sp1[m] * u2; }       // e*u^3 ; 3e*u^2
                                 lA[m] = fmaf(d, d, lA[m]);
-                                float first = d;
-                                if (has_fhat) first = d + fh;
-                                const float w2 = first * (sp1[m] * u2);
+                                first[m] = has_fhat ? d + fh : d;          // the update ignores fhat (N3)
+                                w2[m] = first[m] * nl;
+                            }
+                            if (has_fhat) fh = slot[fhoff + rn];
 #pragma unroll
-                                for (int k = 0; k < N; ++k) {
-                                    g[m][k] = fmaf(first, Tv[k], g[m][k]);
-                                    g[m][k] = fmaf(w2, Pv[k], g[m][k]);
-                                }
+                            for (int q = 0; q < NQT; ++q) {
+#pragma unroll
+                                for (int m = 0; m < M; ++m)
+#pragma unroll
+                                    for (int kk = 0; kk < 4; ++kk) {
+                                        const int k = 4 * q + kk;
+                                        if (k < N) {
+                                            g[m][k] = fmaf(first[m], Tv[k], g[m][k]);
+                                            g[m][k] = fmaf(w2[m], Pv[k], g[m][k]);
+                                        }
+                                    }
+                                load_quad<RT>(Tw, rn, q, Tv);
+                                if (q < NQ) load_quad<RT>(Pblk, rn, q, Pv);
                             }
                         }
                     }
@@ -260,13 +311,13 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
             for (int t = 0; t < p.ntile[1]; ++t) {
                 const float *slot = acquire();
                 if (active) {
-                    for (int r = slice; r < R_TILE; r += RL) {
+                    for (int r = slice; r < RT; r += RL) {
                         float Av[4 * NQ];
-                        load_row<NQ>(slot, r, Av);
+                        load_row<NQ, RT>(slot, r, Av);
                         const float tg = slot[VEC0 + r];
                         if constexpr (PDE == PDE_KG) {
                             float Bv[4 * NQ];
-                            load_row<NQ>(slot + ARR_FLTS, r, Bv);
+                            load_row<NQ, RT>(slot + ARR, r, Bv);
                             const float tg2 = slot[VEC1 + r];
 #pragma unroll
                             for (int m = 0; m < M; ++m) {
@@ -302,13 +353,13 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                 for (int t = 0; t < p.ntile[seg]; ++t) {
                     const float *slot = acquire();
                     if (active) {
-                        for (int r = slice; r < R_TILE; r += RL) {
+                        for (int r = slice; r < RT; r += RL) {
                             float Av[4 * NQ];
-                            load_row<NQ>(slot, r, Av);
+                            load_row<NQ, RT>(slot, r, Av);
                             if constexpr (PDE == PDE_AC) {     // periodic: (P_ub c - P_lb c) * P_diff
                                 float Bv[4 * NQ], Dv[4 * NQ];
-                                load_row<NQ>(slot + ARR_FLTS, r, Bv);
-                                load_row<NQ>(slot + 2 * ARR_FLTS, r, Dv);
+                                load_row<NQ, RT>(slot + ARR, r, Bv);
+                                load_row<NQ, RT>(slot + 2 * ARR, r, Dv);
 #pragma unroll
                                 for (int m = 0; m < M; ++m) {
                                     const float d = dotn<N>(Av, c[m], 0.f) - dotn<N>(Bv, c[m], 0.f);
@@ -383,33 +434,46 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                 }
             }
         }
-    }   // rounds
+    }   // items
+
+    if (PRIV) {     // drain: NST tiles are always in flight; no bulk copy may outlive the CTA
+        for (int k = 0; k < NST; ++k) { mbar_wait(&full[gt % NST], (gt / NST) & 1); ++gt; }
+    }
 }
 
 // host-side launcher signature shared by the per-(PDE, n) translation units
-typedef cudaError_t (*sweep_launch_fn)(const SweepParams &p, int M, int ctas, size_t smem, cudaStream_t st);
+typedef cudaError_t (*sweep_launch_fn)(const SweepParams &p, int M, int priv, int ctas, size_t smem, cudaStream_t st);
 
-template <int PDE, int N, int M, int MAXW>
+template <int PDE, int N, int M, int MAXW, bool PRIV>
 cudaError_t launch_one(const SweepParams &p, int ctas, size_t smem, cudaStream_t st)
 {
-    auto kern = sweep_kernel<PDE, N, M, MAXW>;
+    auto kern = sweep_kernel<PDE, N, M, MAXW, PRIV>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<ctas, p.W * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 
-// warps-per-CTA ceiling for each M (register budget: 64K regs / (32 * W) per thread)
+// warps-per-CTA ceiling for each M (register budget; allocation granularity is 4 warps)
 constexpr int maxw_for_m(int M) { return M >= 4 ? 8 : (M == 3 ? 12 : 16); }
 
 template <int PDE, int N>
-cudaError_t launch_n(const SweepParams &p, int M, int ctas, size_t smem, cudaStream_t st)
+cudaError_t launch_n(const SweepParams &p, int M, int priv, int ctas, size_t smem, cudaStream_t st)
 {
+    if (priv) {
+        switch (M) {
+            case 1: return launch_one<PDE, N, 1, maxw_for_m(1), true>(p, ctas, smem, st);
+            case 2: return launch_one<PDE, N, 2, maxw_for_m(2), true>(p, ctas, smem, st);
+            case 4: return launch_one<PDE, N, 4, maxw_for_m(4), true>(p, ctas, smem, st);
+            case 5: return launch_one<PDE, N, 5, maxw_for_m(5), true>(p, ctas, smem, st);
+            default: return cudaErrorInvalidValue;
+        }
+    }
     switch (M) {
-        case 1: return launch_one<PDE, N, 1, maxw_for_m(1)>(p, ctas, smem, st);
-        case 2: return launch_one<PDE, N, 2, maxw_for_m(2)>(p, ctas, smem, st);
-        case 4: return launch_one<PDE, N, 4, maxw_for_m(4)>(p, ctas, smem, st);
-        case 5: return launch_one<PDE, N, 5, maxw_for_m(5)>(p, ctas, smem, st);
+        case 1: return launch_one<PDE, N, 1, maxw_for_m(1), false>(p, ctas, smem, st);
+        case 2: return launch_one<PDE, N, 2, maxw_for_m(2), false>(p, ctas, smem, st);
+        case 4: return launch_one<PDE, N, 4, maxw_for_m(4), false>(p, ctas, smem, st);
+        case 5: return launch_one<PDE, N, 5, maxw_for_m(5), false>(p, ctas, smem, st);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -97,6 +97,7 @@ def _run(fn_name, prob, keep, grid, gcols, n, c0, epochs, lr, rec_every, want_c,
     args.trace_dev = trace.data_ptr() if trace is not None else None
     if cfg:
         args.cfg_M, args.cfg_SL, args.cfg_W = (int(cfg.get("M", 0)), int(cfg.get("SL", 0)), int(cfg.get("W", 0)))
+        args.cfg_mode = int(cfg.get("mode", 0))
     info = SweepInfo()
     with torch.cuda.device(device):
         h = _lib.handle(device.index if device.index is not None else torch.cuda.current_device())

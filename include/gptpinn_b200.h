@@ -110,6 +110,7 @@ typedef struct {
     /* tuning override, 0 = let the library choose: parameters per thread (M), sibling lanes
      * per warp (SL, power of two <= 32), warps per CTA (W).                                   */
     int           cfg_M, cfg_SL, cfg_W;
+    int           cfg_mode;    /* 0 = auto, 1 = shared-ring kernel, 2 = private-ring kernel      */
 } gptpinn_sweep_args;
 
 /* filled by the sweep calls when non-NULL: what was launched (for bench.py / tests)           */
@@ -121,6 +122,7 @@ typedef struct {
     int   kernels_launched;    /* sweep + pack kernels enqueued by this call                   */
     int   smem_bytes;
     int   tiles_per_pass;
+    int   priv;                /* 1 = private-ring kernel (dynamic tickets), 0 = shared ring    */
 } gptpinn_sweep_info;
 
 int  gptpinn_version(void);

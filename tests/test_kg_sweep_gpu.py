@@ -48,15 +48,21 @@ def test_kg_matches_reference_golden(case):
         assert abs(float(L) - float(g[f"n{n}_L"])) <= TOL * float(g[f"n{n}_L"])
 
 
-@pytest.mark.parametrize("cfg", [dict(M=1, SL=1), dict(M=1, SL=32), dict(M=2, SL=4), dict(M=4, SL=2),
-                                 dict(M=5, SL=1), dict(M=5, SL=8, W=3), dict(M=2, SL=16, W=16)])
+@pytest.mark.parametrize("cfg", [dict(M=1, SL=1, mode=1), dict(M=1, SL=32, mode=1), dict(M=2, SL=4, mode=1),
+                                 dict(M=4, SL=2, mode=1), dict(M=5, SL=1, mode=1), dict(M=5, SL=8, W=3, mode=1),
+                                 dict(M=2, SL=16, W=16, mode=1),
+                                 dict(M=1, SL=1, mode=2), dict(M=1, SL=32, mode=2), dict(M=2, SL=4, mode=2),
+                                 dict(M=4, SL=2, mode=2), dict(M=5, SL=1, mode=2), dict(M=5, SL=8, W=3, mode=2),
+                                 dict(M=5, mode=2), dict(M=4, mode=2), dict(M=2, mode=2), dict(mode=1), dict(mode=2)])
 def test_kg_every_mapping_agrees(cfg):
     """All (M, SL, W) mappings compute the same thing (different summation trees only)."""
     g = load_golden("kg_small")
     d = _dev(g, KG_NAMES)
     for n in (2, 15):
         r = _run(d, n, g["grid"], int(g["epochs"]), lr_of(g, 0), cfg=cfg)
-        assert r["info"]["M"] == cfg["M"] and r["info"]["SL"] == cfg["SL"]
+        if "M" in cfg:
+            assert r["info"]["M"] == cfg["M"]
+        assert r["info"]["priv"] == cfg["mode"] - 1
         assert rel_scalar(r["f"].cpu().numpy(), g[f"n{n}_f"]) < TOL
         assert rel_vec(r["c"].cpu().numpy(), g[f"n{n}_c"]) < TOL
 

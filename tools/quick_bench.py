@@ -34,8 +34,8 @@ def main():
     _lib.check(_lib.lib().gptpinn_ffma_peak(C.byref(tf), 3, None), "peak")
     print("FFMA peak measured TFLOP/s:", tf.value, flush=True)
     W_n = 8 * n * NR + 4 * n * (NB + 2 * NI)
-    cfgs = [None] + [dict(M=int(m), SL=int(s), W=int(w)) for m, s, w in
-                     (c.split(":") for c in os.environ.get("QB_CFGS", "5:8:8,5:4:8,5:2:8,4:8:8,2:16:16,2:8:16").split(","))]
+    cfgs = [None] + [dict(M=int(m), SL=int(s), W=int(w), mode=int(md)) for m, s, w, md in
+                     (c.split(":") for c in os.environ.get("QB_CFGS", "5:8:8:1,5:8:8:2,5:0:8:2,5:4:8:2,4:8:8:2,2:0:16:2").split(","))]
     for cfg in cfgs:
         def run():
             return sweep.kg_sweep(grid, c0, out[:, :n], out_xx[:, :n], out_tt[:, :n], out_IC[:, :n], out_IC_t[:, :n],
