@@ -235,7 +235,9 @@ static int make_plan(std::vector<ParamRow> &rows, int pde, int n, int n_sm, cons
         const int maxw = maxw_for_m(M);
         // ---- private rings: dynamic tickets, mixed item sizes ----
         if (mode != 1) {
-            const int W = a->cfg_W > 0 ? std::min(a->cfg_W, maxw) : maxw;
+            const int wsmem = (int)((227.0 * 1024 - 64) / (NST_PRIV * slot_p + (n / 4 + 1) * 4 * RT_PRIV * 4 + NST_PRIV * 8));
+            const int maxwp = std::max(1, std::min(maxw, wsmem));
+            const int W = a->cfg_W > 0 ? std::min(a->cfg_W, maxwp) : maxwp;
             const int workers = n_sm * W;
             if (a->cfg_SL > 0) {
                 ch.clear();
