@@ -1,0 +1,73 @@
+"""Drop-in for Allen-Cahn/AC_models.py: GPT_residual (reference AC_models.py:6-10), GPT
+(AC_models.py:12-54) and P (AC_models.py:56-78, the tanh [2,128,128,128,128,1] shell that
+receives the weights of the trained SA-PINN)."""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from _common import precomp, sweep
+
+device = torch.device("cuda")
+
+
+def GPT_residual(c, eps, out, Pt_lPxx_eP_term):
+    u = torch.matmul(out, c)
+    return torch.add(torch.matmul(Pt_lPxx_eP_term, c), torch.mul(eps, torch.pow(u, 3)))
+
+
+class GPT(nn.Module):
+    def __init__(self, lmbda, eps, out, out_IC, out_BC_ub, out_BC_lb,
+                 out_BC_ub_x, out_BC_lb_x, fhat, Pt_lPxx_eP_term, IC_u):
+        super().__init__()
+        self.lmbda, self.eps = lmbda, eps
+        self.loss_function = nn.MSELoss(reduction='mean')
+        self.IC_u, self.fhat = IC_u, fhat
+        self.Pt_lPxx_eP_term = Pt_lPxx_eP_term
+        self.out_IC, self.out = out_IC, out
+        self.out_BC_ub, self.out_BC_lb = out_BC_ub, out_BC_lb
+        self.out_BC_ub_x, self.out_BC_lb_x = out_BC_ub_x, out_BC_lb_x
+
+    def lossR(self, c):
+        return self.loss_function(GPT_residual(c, self.eps, self.out, self.Pt_lPxx_eP_term), self.fhat)
+
+    def lossBC(self, c):
+        return self.loss_function(self.out_BC_ub @ c, self.out_BC_lb @ c)
+
+    def lossBC_x(self, c):
+        return self.loss_function(self.out_BC_ub_x @ c, self.out_BC_lb_x @ c)
+
+    def lossIC(self, c):
+        return self.loss_function(self.out_IC @ c, self.IC_u)
+
+    def loss(self, c):
+        Pt = torch.add(self.Pt_lPxx_eP_term, torch.mul(self.eps, self.out))
+        grid = np.array([[0.0, float(self.eps)]])
+        r = sweep.ac_sweep(grid, c.reshape(-1), self.out, Pt, Pt, self.out_IC, self.out_BC_ub, self.out_BC_lb,
+                           self.out_BC_ub, self.out_BC_ub_x, self.out_BC_lb_x, self.out_BC_ub_x, self.fhat,
+                           self.IC_u, 0, 0.0, want_c=False)
+        return r["f"][0]
+
+
+class P(nn.Module):
+    def __init__(self, w, b, layers):
+        super().__init__()
+        self.layers = layers
+        self.linears = nn.ModuleList([nn.Linear(int(layers[i]), int(layers[i + 1])) for i in range(len(layers) - 1)])
+        for i in range(len(w) - 1):
+            self.linears[i].weight.data = w[i]
+        self.linears[-1].weight.data = torch.Tensor(w[-1]).view(1, int(layers[-2]))
+        for i in range(len(b) - 1):
+            self.linears[i].bias.data = b[i]
+        self.linears[-1].bias.data = torch.Tensor(b[-1]).view(-1)
+        self.activation = nn.Tanh()
+        self.activation_name = "tanh"
+
+    def forward(self, x):
+        if x.is_cuda and not (torch.is_grad_enabled() and (x.requires_grad or self.linears[0].weight.requires_grad)):
+            u = torch.empty((x.shape[0], 1), dtype=torch.float32, device=x.device)
+            precomp.mlp_channels(self, "tanh", x, v=u)
+            return u
+        a = x
+        for lin in self.linears[:-1]:
+            a = torch.tanh(lin(a))
+        return self.linears[-1](a)

@@ -1,0 +1,77 @@
+"""Drop-in for Klein-Gordon/KG_test.py.
+
+gpt_test / gpt_test_loss (reference KG_test.py:10-44, 49-76): the per-test-parameter loop of 5000
+updates is ONE fused launch over all test parameters; gpt_test_loss reads the loss trace the
+kernel records every 500 epochs.  pinn_test / pinn_test_loss (KG_test.py:81-140) train one full
+PINN per test parameter.
+"""
+import time
+
+import numpy as np
+import torch
+
+from KG_models import NN
+from _common import offline, pinn, sweep
+
+device = torch.device("cuda")
+
+
+def gpt_test(kg_test, out, out_xx, out_tt, out_IC, out_IC_t, out_BC, fhat,
+             xcos, xt_len, IC_size, BC_size, IC_u1, IC_u2, BC_u, c_initial,
+             epochs_gpt, lr_gpt, U_test):
+    t0 = time.time()
+    grid = np.asarray(kg_test, dtype=np.float64).reshape(-1, 3)
+
+    def run(rows, _c0):
+        return sweep.kg_sweep(rows, c_initial, out, out_xx, out_tt, out_IC, out_IC_t, out_BC, xcos, fhat,
+                              IC_u1, IC_u2, BC_u, epochs_gpt, lr_gpt, want_c=True)
+
+    res = offline.sharded_sweep(run, grid, want_c=True, gather_c=True, group_cols=(0, 1))
+    soln = torch.matmul(U_test, res["c"].t())                 # [N_test, n_cases]
+    gpt_soln = soln.detach().cpu().numpy().astype(np.float64)
+    times = offline.spread_hours(time.time() - t0, len(grid))
+    return times, gpt_soln
+
+
+def gpt_test_loss(kg_test, out, out_xx, out_tt, out_IC, out_IC_t, out_BC, fhat,
+                  xcos, xt_len, IC_size, BC_size, IC_u1, IC_u2, BC_u,
+                  c_initial, epochs_gpt, lr_gpt):
+    grid = np.asarray(kg_test, dtype=np.float64).reshape(-1, 3)
+    lo, hi = offline.shard_bounds(len(grid))
+    r = sweep.kg_sweep(grid[lo:hi], c_initial, out, out_xx, out_tt, out_IC, out_IC_t, out_BC, xcos, fhat,
+                       IC_u1, IC_u2, BC_u, epochs_gpt, lr_gpt, rec_every=500, want_c=False)
+    trace = offline.gather_rows(r["trace"], len(grid))        # [n_cases, epochs/500 + 1]
+    losses = np.zeros((11, len(grid)))
+    tr = trace.t().cpu().numpy().astype(np.float64)
+    losses[:min(11, tr.shape[0])] = tr[:11]
+    return losses
+
+
+def pinn_test(kg_test, layers_pinn, xcos_x2cos2, xt_resid, IC_xt, IC_u1, IC_u2,
+              BC_xt, BC_u, f_hat, epochs_pinn, lr_pinn, xt_test):
+    times = np.zeros(len(kg_test))
+    pinn_soln = np.zeros((xt_test.shape[0], len(kg_test)))
+    for i, (alpha, beta, gamma) in enumerate(kg_test):
+        t_start = time.time()
+        PINN = NN(layers_pinn, alpha, beta, gamma, xcos_x2cos2).to(device)
+        pinn.train_adam(PINN, lambda: PINN.loss(xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u),
+                        epochs_pinn, lr_pinn)
+        with torch.no_grad():
+            soln = PINN(xt_test)
+        dt = (time.time() - t_start) / 3600
+        times[i] = dt if i == 0 else dt + times[i - 1]
+        pinn_soln[:, i][:, None] = soln.detach().cpu().numpy()
+    return times, pinn_soln
+
+
+def pinn_test_loss(kg_test, layers_pinn, xcos_x2cos2, xt_resid, IC_xt, IC_u1,
+                   IC_u2, BC_xt, BC_u, f_hat, epochs_pinn, lr_pinn):
+    losses = np.zeros((101, len(kg_test)))
+    for i, (alpha, beta, gamma) in enumerate(kg_test):
+        PINN = NN(layers_pinn, alpha, beta, gamma, xcos_x2cos2).to(device)
+        loss_fn = lambda: PINN.loss(xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u)  # noqa: E731
+        losses[0, i] = loss_fn().item()
+        rec = pinn.train_adam(PINN, loss_fn, epochs_pinn, lr_pinn, record_every=1000)
+        for j, v in rec.items():
+            losses[int(j / 1000), i] = v
+    return losses

@@ -201,7 +201,200 @@ def gen_kg_full():
     kg_case("kg_full", 100, 512, 512, 40, [15], grid[sel], 2000, 0.025, 500, None, 0)
 
 
-GENS = {"kg_small": gen_kg_small, "kg_nonmono": gen_kg_nonmono, "kg_full": gen_kg_full}
+# --------------------------------------------------------------------------------------
+# generic trajectory driver (the loop of *_train.offline_generation without the early exit)
+# --------------------------------------------------------------------------------------
+def trajectories(make_pair, grid, c0_of, n, epochs, rec_every):
+    nrec = epochs // rec_every + 1
+    C = np.zeros((len(grid), n), np.float32)
+    F = np.zeros(len(grid), np.float32)
+    M = np.zeros(len(grid), np.float32)
+    T = np.zeros((len(grid), nrec), np.float32)
+    for gi, mu in enumerate(grid):
+        GD, NNg = make_pair(mu)
+        c = c0_of(gi)
+        cr = c.unsqueeze(1)
+        loss = NNg.loss(cr)
+        mp = float("inf")
+        T[gi, 0] = loss.item()
+        for j in range(1, epochs + 1):
+            mp = min(mp, loss.item())
+            c = GD.update(c, cr)
+            cr = c.unsqueeze(1)
+            loss = NNg.loss(cr)
+            if j % rec_every == 0:
+                T[gi, j // rec_every] = loss.item()
+        C[gi] = c.numpy()
+        F[gi] = loss.item()
+        M[gi] = mp
+    return C, F, M, T
+
+
+# --------------------------------------------------------------------------------------
+# Burgers
+# --------------------------------------------------------------------------------------
+def gen_b_small():
+    m = _import_ref("Burgers", ["B_data", "B_models", "B_precomp", "B_optimizer", "B_train", "B_test"])
+    Nc, N_test, BC_pts, IC_pts, nmax = 24, 10, 40, 40, 9
+    xt_resid, f_hat, xt_test = m["B_data"].residual_data(-1.0, 1.0, 0.0, 1.0, Nc, N_test)
+    IC_xt, IC_u, BC_xt, BC_u = m["B_data"].ICBC_data(-1.0, 1.0, 0.0, 1.0, BC_pts, IC_pts)
+    xt_resid = xt_resid.requires_grad_()
+    N, NI, NB, NT = xt_resid.shape[0], IC_xt.shape[0], BC_xt.shape[0], xt_test.shape[0]
+    z = lambda r: torch.zeros(r, nmax)
+    out, out_t, out_x, out_xx, out_IC, out_BC, out_test = z(N), z(N), z(N), z(N), z(NI), z(NB), z(NT)
+    num_mag = int(N * 0.2)
+    idx_list = torch.zeros((nmax, num_mag), dtype=torch.long)
+    layers = np.array([2, 20, 20, 20, 20, 1])
+    neurons = np.linspace(0.005, 1, 129)[[64, 0, 128, 20, 100, 40, 80, 10, 118]]
+    save = {}
+    for i in range(nmax):
+        pinn = m["B_models"].NN(layers, neurons[i])
+        _randomize(pinn, 2000 + i, scale=1.0, pert=0.05)
+        for k, a in _weights(pinn).items():
+            save[f"pinn{i}_{k}"] = a
+        m["B_precomp"].inputs(pinn, xt_resid, out, out_t, out_x, out_xx, out_IC, out_BC, IC_xt, BC_xt, i,
+                              out_test, xt_test, N, num_mag, idx_list)
+    bufs = dict(out=out, out_t=out_t, out_x=out_x, out_xx=out_xx, out_IC=out_IC, out_BC=out_BC, out_test=out_test)
+    bufs = {k: v.detach() for k, v in bufs.items()}
+    save.update({k: v.numpy() for k, v in bufs.items()})
+    save.update(xt_resid=xt_resid.detach().numpy(), xt_test=xt_test.numpy(), IC_xt=IC_xt.numpy(), BC_xt=BC_xt.numpy(),
+                IC_u=IC_u.numpy(), BC_u=BC_u.numpy(), f_hat=f_hat.numpy(), idx_list=idx_list.numpy(), neurons=neurons)
+    grid = np.delete(np.linspace(0.005, 1, 33), [16])
+    ns, epochs, lr, rec = [1, 2, 5, 9], 300, 0.02, 50
+    save.update(grid=grid, ns=np.array(ns), epochs=epochs, lr=lr, rec_every=rec)
+    for n in ns:
+        v = {k: bufs[k][:, :n] for k in ("out", "out_t", "out_x", "out_xx", "out_IC", "out_BC")}
+        # initial c per parameter exactly as B_train.offline_generation builds it (B_train.py:27-47)
+        c0s = []
+        for nu in grid:
+            if n == 1:
+                c0s.append(torch.ones(1))
+                continue
+            dist = np.abs(neurons[:n] - nu)
+            d = np.argsort(dist)
+            c0 = torch.zeros(n)
+            c0[d[0]] = dist[d[1]] / (dist[d[0]] + dist[d[1]])
+            c0[d[1]] = dist[d[0]] / (dist[d[0]] + dist[d[1]])
+            c0s.append(c0)
+
+        def make_pair(nu):
+            T = m["B_precomp"].Pt_nu_P_xx(nu, v["out_t"], v["out_xx"])
+            GD = m["B_optimizer"].grad_descent(nu, N, NI, NB, IC_u, v["out"], v["out_IC"], v["out_BC"], v["out_x"], T, lr)
+            NNg = m["B_models"].GPT(nu, v["out"], v["out_IC"], v["out_BC"], v["out_x"], T, IC_u, BC_u, f_hat)
+            return GD, NNg
+        C, F, M, T = trajectories(make_pair, grid, lambda gi: c0s[gi], n, epochs, rec)
+        L, case = m["B_train"].offline_generation(grid, N, NI, NB, IC_u, BC_u, v["out"], v["out_x"], v["out_t"],
+                                                  v["out_xx"], v["out_IC"], v["out_BC"], f_hat, epochs, lr, neurons, n - 1)
+        save[f"n{n}_c0"] = np.stack([c.numpy() for c in c0s])
+        save[f"n{n}_c"], save[f"n{n}_f"], save[f"n{n}_m"], save[f"n{n}_trace"] = C, F, M, T
+        save[f"n{n}_L"] = np.float32(float(L))
+        save[f"n{n}_case"] = np.float64(case)
+        print("b_small n", n, "L", float(L), "case", case, flush=True)
+    test_nu = grid[[3, 11, 29]]
+    times, soln = m["B_test"].gpt_test(test_nu, N, NI, NB, IC_u, BC_u, bufs["out"], bufs["out_x"], bufs["out_t"],
+                                       bufs["out_xx"], bufs["out_IC"], bufs["out_BC"], f_hat, 1000, lr, neurons,
+                                       bufs["out_test"])
+    losses = m["B_test"].gpt_test_loss(test_nu, N, NI, NB, IC_u, BC_u, bufs["out"], bufs["out_x"], bufs["out_t"],
+                                       bufs["out_xx"], bufs["out_IC"], bufs["out_BC"], f_hat, 1000, lr, neurons)
+    save.update(test_mu=test_nu, test_epochs=1000, test_soln=soln, test_losses=losses)
+    np.savez_compressed(os.path.join(OUT, "b_small.npz"), **save)
+    print("wrote b_small")
+
+
+# --------------------------------------------------------------------------------------
+# Allen-Cahn (GPT / precompute path only: AC_main.py itself needs TensorFlow + pyDOE)
+# --------------------------------------------------------------------------------------
+def gen_ac_small():
+    import scipy.io
+    m = _import_ref("Allen-Cahn", ["AC_models", "AC_precompute", "AC_optimizer", "AC_train", "AC_test"])
+    rng = np.random.default_rng(0)
+    N, NI, NB, nmax = 800, 64, 20, 9
+    data = scipy.io.loadmat(os.path.join(REF, "Allen-Cahn", "AC.mat"))
+    x = data["x"].flatten()[:, None]
+    t = data["tt"].flatten()[:, None]
+    uu = data["uu"]
+    idx_x = np.sort(rng.choice(x.shape[0], NI, replace=False))
+    IC_xt = torch.tensor(np.hstack((x[idx_x], 0 * x[idx_x])), dtype=torch.float32)
+    IC_u = torch.tensor(uu[idx_x, 0:1], dtype=torch.float32)
+    tb = t[rng.choice(t.shape[0], NB, replace=False)]
+    BC_xt_ub = torch.tensor(np.hstack((0 * tb + 1.0, tb)), dtype=torch.float32).requires_grad_()
+    BC_xt_lb = torch.tensor(np.hstack((0 * tb - 1.0, tb)), dtype=torch.float32).requires_grad_()
+    xt = torch.tensor(np.hstack((rng.uniform(-1, 1, (N, 1)), rng.uniform(0, 1, (N, 1)))), dtype=torch.float32).requires_grad_()
+    f_hat = torch.zeros(N, 1)
+    xg, tg = torch.meshgrid((torch.linspace(-1, 1, 12), torch.linspace(0, 1, 12)), indexing="ij")
+    xt_test = torch.hstack((xg.transpose(1, 0).flatten().unsqueeze(1), tg.transpose(1, 0).flatten().unsqueeze(1)))
+    NT = xt_test.shape[0]
+    z = lambda r: torch.zeros(r, nmax)
+    out, out_t, out_xx, out_IC, out_test = z(N), z(N), z(N), z(NI), z(NT)
+    ub, lb, df, ubx, lbx, dfx = z(NB), z(NB), z(NB), z(NB), z(NB), z(NB)
+    layers = [2, 128, 128, 128, 128, 1]
+    save = {}
+    for i in range(nmax):
+        g = torch.Generator().manual_seed(3000 + i)
+        w, b = [], []
+        for l in range(len(layers) - 1):
+            fi, fo = layers[l], layers[l + 1]
+            std = (2.0 / (fi + fo)) ** 0.5
+            w.append((torch.randn(fo, fi, generator=g) * std * 1.2).float())
+            b.append((torch.randn(fo, generator=g) * 0.1).float())
+        pinn = m["AC_models"].P(w, b, layers)
+        if i < 2:
+            for l in range(len(layers) - 1):
+                save[f"pinn{i}_W{l}"] = pinn.linears[l].weight.data.numpy().copy()
+                save[f"pinn{i}_b{l}"] = pinn.linears[l].bias.data.numpy().copy()
+        m["AC_precompute"].inputs(pinn, xt, out, out_xx, out_t, out_IC, ub, lb, IC_xt, BC_xt_ub, BC_xt_lb, i,
+                                  out_test, xt_test, f_hat, N, df, ubx, lbx, dfx)
+    bufs = dict(out=out, out_t=out_t, out_xx=out_xx, out_IC=out_IC, out_test=out_test, out_BC_ub=ub, out_BC_lb=lb,
+                out_BC_diff=df, out_BC_ub_x=ubx, out_BC_lb_x=lbx, out_BC_diff_x=dfx)
+    bufs = {k: v.detach() for k, v in bufs.items()}
+    save.update({k: v.numpy() for k, v in bufs.items()})
+    save.update(xt_resid=xt.detach().numpy(), xt_test=xt_test.numpy(), IC_xt=IC_xt.numpy(),
+                BC_xt_ub=BC_xt_ub.detach().numpy(), BC_xt_lb=BC_xt_lb.detach().numpy(), IC_u=IC_u.numpy(),
+                f_hat=f_hat.numpy())
+    lm = np.linspace(1e-3, 1e-4, 5)
+    ep = np.linspace(1, 5, 5)
+    grid = np.array(np.meshgrid(lm, ep)).T.reshape(-1, 2)          # AC_main.py:115-117 ordering
+    ns, epochs, lr, rec = [1, 3, 9], 300, 0.0025, 50
+    save.update(grid=grid, ns=np.array(ns), epochs=epochs, lr=lr, rec_every=rec)
+    names = ("out", "out_t", "out_xx", "out_IC", "out_BC_ub", "out_BC_lb", "out_BC_diff", "out_BC_ub_x",
+             "out_BC_lb_x", "out_BC_diff_x")
+    for n in ns:
+        v = {k: bufs[k][:, :n] for k in names}
+        c0 = torch.full((n,), 1.0 / n)
+
+        def make_pair(mu):
+            lam, eps = mu
+            T = m["AC_precompute"].Pt_lPxx_eP(v["out_t"], v["out_xx"], v["out"], lam, eps)
+            GD = m["AC_optimizer"].grad_descent(lam, eps, N, NI, NB, IC_u, T, v["out"], v["out_IC"], v["out_BC_ub"],
+                                                v["out_BC_lb"], v["out_BC_diff"], v["out_BC_ub_x"], v["out_BC_lb_x"],
+                                                v["out_BC_diff_x"], epochs, lr)
+            NNg = m["AC_models"].GPT(lam, eps, v["out"], v["out_IC"], v["out_BC_ub"], v["out_BC_lb"],
+                                     v["out_BC_ub_x"], v["out_BC_lb_x"], f_hat, T, IC_u)
+            return GD, NNg
+        C, F, M, T = trajectories(make_pair, grid, lambda gi: c0, n, epochs, rec)
+        L, case, tc = m["AC_train"].offline_generation(grid, c0, N, NI, NB, IC_u, v["out"], v["out_t"], v["out_xx"],
+                                                       v["out_IC"], v["out_BC_ub"], v["out_BC_lb"], v["out_BC_diff"],
+                                                       v["out_BC_ub_x"], v["out_BC_lb_x"], v["out_BC_diff_x"], f_hat,
+                                                       epochs, lr)
+        save[f"n{n}_c"], save[f"n{n}_f"], save[f"n{n}_m"], save[f"n{n}_trace"] = C, F, M, T
+        save[f"n{n}_L"] = np.float32(float(L))
+        save[f"n{n}_case"] = np.array(case, np.float64)
+        save[f"n{n}_trained_c"] = tc.numpy()
+        print("ac_small n", n, "L", float(L), "case", case, flush=True)
+    test_mu = grid[[2, 13, 21]]
+    c0 = torch.full((nmax,), 1.0 / nmax)
+    args = (bufs["out"], bufs["out_t"], bufs["out_xx"], bufs["out_IC"], f_hat, N, NI, NB, IC_u, c0, 400, lr,
+            bufs["out_test"], bufs["out_BC_ub"], bufs["out_BC_lb"], bufs["out_BC_diff"], bufs["out_BC_ub_x"],
+            bufs["out_BC_lb_x"], bufs["out_BC_diff_x"])
+    times, soln = m["AC_test"].gpt_test(test_mu, *args)
+    losses = m["AC_test"].gpt_test_loss(test_mu, *args)
+    save.update(test_mu=test_mu, test_epochs=400, test_soln=soln, test_losses=losses)
+    np.savez_compressed(os.path.join(OUT, "ac_small.npz"), **save)
+    print("wrote ac_small")
+
+
+GENS = {"kg_small": gen_kg_small, "kg_nonmono": gen_kg_nonmono, "kg_full": gen_kg_full,
+        "b_small": gen_b_small, "ac_small": gen_ac_small}
 
 if __name__ == "__main__":
     torch.set_num_threads(int(os.environ.get("OMP_NUM_THREADS", "8")))

@@ -50,3 +50,12 @@ def rel_scalar(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-30)))
+
+
+def selection_ok(f_ref, idx_ref, idx, tie_tol=1e-6):
+    """Identical selection, except when the reference's own losses tie within `tie_tol` relative
+    (a couple of fp32 ulps): then any of the tied parameters is accepted and the tie is reported."""
+    if idx == idx_ref:
+        return True
+    f_ref = np.asarray(f_ref, np.float64)
+    return idx >= 0 and abs(f_ref[idx] - f_ref[idx_ref]) <= tie_tol * abs(f_ref[idx_ref])

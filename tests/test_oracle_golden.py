@@ -6,7 +6,7 @@ arg-max selection.  The f64 build is the adjudicator and must agree to the same 
 import numpy as np
 import pytest
 
-from conftest import load_golden, lr_of, rel_scalar, rel_vec
+from conftest import load_golden, lr_of, rel_scalar, rel_vec, selection_ok
 from oracle import oracle
 
 TOL = 1e-5
@@ -64,3 +64,133 @@ def test_scan_semantics_small_cases():
     assert oracle.argmax_scan(f, m) == (3.0, 1)
     assert oracle.argmax_scan(np.zeros(4, np.float32), np.zeros(4, np.float32)) == (0.0, -1)
     assert oracle.argmax_scan(np.array([], np.float32), np.array([], np.float32)) == (0.0, -1)
+
+
+# ---------------------------------------------------------------------------------------------
+# Burgers / Allen-Cahn
+# ---------------------------------------------------------------------------------------------
+def _b_prob(g, n):
+    return oracle.b_problem(n, g["out"], g["out_x"], g["out_t"], g["out_xx"], g["out_IC"], g["out_BC"],
+                            g["f_hat"], g["IC_u"], g["BC_u"])
+
+
+def _ac_prob(g, n):
+    return oracle.ac_problem(n, g["out"], g["out_t"], g["out_xx"], g["out_IC"], g["out_BC_ub"], g["out_BC_lb"],
+                             g["out_BC_diff"], g["out_BC_ub_x"], g["out_BC_lb_x"], g["out_BC_diff_x"],
+                             g["f_hat"], g["IC_u"])
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_burgers_trajectories_match_reference(prec):
+    g = load_golden("b_small")
+    for i, n in enumerate(g["ns"]):
+        n = int(n)
+        r = oracle.sweep("b", _b_prob(g, n), g["grid"], g[f"n{n}_c0"], int(g["epochs"]), lr_of(g, i),
+                         int(g["rec_every"]), prec)
+        assert rel_scalar(r["f"], g[f"n{n}_f"]) < TOL
+        assert rel_scalar(r["m"], g[f"n{n}_m"]) < TOL
+        assert rel_vec(r["c"], g[f"n{n}_c"]) < TOL
+        assert rel_scalar(r["trace"], g[f"n{n}_trace"]) < TOL
+        L, idx = oracle.argmax_scan(r["f"], r["m"])
+        assert g["grid"][idx] == float(g[f"n{n}_case"])
+        assert abs(L - float(g[f"n{n}_L"])) <= TOL * L
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_allen_cahn_trajectories_match_reference(prec):
+    g = load_golden("ac_small")
+    for i, n in enumerate(g["ns"]):
+        n = int(n)
+        r = oracle.sweep("ac", _ac_prob(g, n), g["grid"], np.full(n, 1.0 / n, np.float32), int(g["epochs"]),
+                         lr_of(g, i), int(g["rec_every"]), prec)
+        assert rel_scalar(r["f"], g[f"n{n}_f"]) < TOL
+        assert rel_scalar(r["m"], g[f"n{n}_m"]) < TOL
+        assert rel_vec(r["c"], g[f"n{n}_c"]) < TOL
+        L, idx = oracle.argmax_scan(r["f"], r["m"])
+        _, iref = oracle.argmax_scan(g[f"n{n}_f"], g[f"n{n}_m"])
+        assert np.array_equal(g["grid"][iref], g[f"n{n}_case"])
+        assert selection_ok(g[f"n{n}_f"], iref, idx)          # n = 1 ties to 2 ulp across lambda
+        assert rel_vec(r["c"][iref][None], g[f"n{n}_trained_c"][None]) < TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# closed-form derivative channels vs the reference's autograd inputs()
+# ---------------------------------------------------------------------------------------------
+PRE_TOL = 2e-5      # fp32 autograd vs closed form evaluated in double; relative to the column's max |.|
+
+
+def _col_err(a, b):
+    a = np.asarray(a, np.float64).reshape(-1)
+    b = np.asarray(b, np.float64).reshape(-1)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+def _weights(g, i):
+    Ws, bs, l = [], [], 0
+    while f"pinn{i}_W{l}" in g:
+        Ws.append(g[f"pinn{i}_W{l}"])
+        bs.append(g[f"pinn{i}_b{l}"])
+        l += 1
+    layers = [Ws[0].shape[1]] + [w.shape[0] for w in Ws]
+    return layers, Ws, bs
+
+
+def test_mlp_channels_kg_matches_reference_inputs():
+    g = load_golden("kg_small")
+    for i in (0, 7, 14):
+        layers, Ws, bs = _weights(g, i)
+        ch = oracle.mlp_channels(layers, Ws, bs, "cos", g["xt_resid"])
+        assert _col_err(ch["v"], g["out"][:, i]) < PRE_TOL
+        assert _col_err(ch["q"], g["out_xx"][:, i]) < PRE_TOL     # u_xx + u_xt  (N2)
+        assert _col_err(ch["r"], g["out_tt"][:, i]) < PRE_TOL     # u_tt + u_xt
+        ic = oracle.mlp_channels(layers, Ws, bs, "cos", g["IC_xt"])
+        assert _col_err(ic["v"], g["out_IC"][:, i]) < PRE_TOL
+        assert _col_err(ic["t"], g["out_IC_t"][:, i]) < PRE_TOL
+        assert _col_err(oracle.mlp_channels(layers, Ws, bs, "cos", g["BC_xt"])["v"], g["out_BC"][:, i]) < PRE_TOL
+        assert _col_err(oracle.mlp_channels(layers, Ws, bs, "cos", g["xt_test"])["v"], g["out_test"][:, i]) < PRE_TOL
+
+
+def test_mlp_channels_burgers_matches_reference_inputs_with_zeroed_rows():
+    g = load_golden("b_small")
+    for i in (0, 4, 8):
+        layers, Ws, bs = _weights(g, i)
+        ch = oracle.mlp_channels(layers, Ws, bs, "tanh", g["xt_resid"])
+        zero = np.zeros(len(ch["v"]), bool)
+        zero[g["idx_list"][i]] = True                               # rows the reference zeroed (B_precomp.py:33-47)
+        # the zeroed set is the 20% largest |P_xx|
+        order = np.argsort(np.abs(ch["q"]), kind="stable")
+        assert set(order[len(order) - zero.sum():]) == set(np.nonzero(zero)[0])
+        for name, key in (("v", "out"), ("x", "out_x"), ("t", "out_t"), ("q", "out_xx")):
+            want = g[key][:, i]
+            assert np.all(want[zero] == 0)
+            assert _col_err(ch[name][~zero], want[~zero]) < PRE_TOL
+
+
+def test_mlp_channels_allen_cahn_matches_reference_inputs():
+    g = load_golden("ac_small")
+    for i in (0, 1):
+        layers, Ws, bs = _weights(g, i)
+        ch = oracle.mlp_channels(layers, Ws, bs, "tanh", g["xt_resid"])
+        assert _col_err(ch["v"], g["out"][:, i]) < PRE_TOL
+        assert _col_err(ch["t"], g["out_t"][:, i]) < PRE_TOL
+        assert _col_err(ch["q"], g["out_xx"][:, i]) < 5 * PRE_TOL   # 4x128-wide tanh stack in fp32 autograd
+        ub = oracle.mlp_channels(layers, Ws, bs, "tanh", g["BC_xt_ub"])
+        lb = oracle.mlp_channels(layers, Ws, bs, "tanh", g["BC_xt_lb"])
+        assert _col_err(ub["v"], g["out_BC_ub"][:, i]) < PRE_TOL
+        assert _col_err(lb["x"], g["out_BC_lb_x"][:, i]) < PRE_TOL
+        assert _col_err(ub["x"] - lb["x"], g["out_BC_diff_x"][:, i]) < 5 * PRE_TOL
+
+
+def test_torch_port_matches_reference():
+    """oracle/torch_port.py (the CPU-baseline timing leg) reproduces the reference bit for bit."""
+    import torch
+    from oracle import torch_port
+    g = load_golden("kg_small")
+    n = 7
+    mats = [torch.from_numpy(g[k][:, :n].copy()) for k in ("out", "out_xx", "out_tt", "out_IC", "out_IC_t", "out_BC")]
+    mats += [torch.from_numpy(g[k]) for k in ("xcos", "f_hat", "IC_u1", "IC_u2", "BC_u")]
+    c0 = torch.full((n,), 1.0 / n)
+    L, idx, _ = torch_port.kg_offline_generation(g["grid"], c0, mats, int(g["epochs"]), lr_of(g, 2))
+    assert float(L) == float(g["n7_L"]) and np.array_equal(g["grid"][idx], g["n7_case"])
+    c, loss = torch_port.kg_trajectory(g["grid"][5], c0, mats, int(g["epochs"]), lr_of(g, 2))
+    assert np.array_equal(c.numpy(), g["n7_c"][5]) and float(loss) == float(g["n7_f"][5])
