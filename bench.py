@@ -330,7 +330,7 @@ def main():
     if not args.no_cpu_baseline:
         mats = host_mats(d)
         threads = os.cpu_count() or 1
-        n_params, ep = 8, 1000
+        n_params, ep = 32, 1000
         v_ref, dt_ref = cpu_reference_rate(mats, grid, n_params, ep, threads)
         cpu = {"value": v_ref, "unit": "param*epochs/s", "cores": threads, "kind": "port",
                "sample": f"{n_params} params x {ep} epochs (update + loss each epoch, no early exit) of the same workload, "

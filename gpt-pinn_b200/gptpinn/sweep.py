@@ -166,8 +166,10 @@ def argmax_scan_device(f, m):
     """Enqueue the exact N1 scan; returns device tensors (L[1] float32, idx[1] int32) without syncing."""
     f = _req_cuda(f, "f").contiguous()
     m = _req_cuda(m, "m").contiguous()
-    L = torch.empty(1, dtype=torch.float32, device=f.device)
-    idx = torch.empty(1, dtype=torch.int32, device=f.device)
+    L = torch.zeros(1, dtype=torch.float32, device=f.device)
+    idx = torch.full((1,), -1, dtype=torch.int32, device=f.device)
+    if f.numel() == 0:
+        return L, idx                      # empty grid: largest_loss stays 0, no case (KG_train.py:12)
     with torch.cuda.device(f.device):
         stream = torch.cuda.current_stream(f.device).cuda_stream
         rc = _lib.lib().gptpinn_argmax_scan(f.data_ptr(), m.data_ptr(), f.numel(), L.data_ptr(), idx.data_ptr(),
