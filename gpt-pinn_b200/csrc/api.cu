@@ -170,7 +170,10 @@ static void decompose(const std::vector<int> &gstart, int M, std::vector<Chunk> 
     std::stable_sort(out.begin(), out.end(), [](const Chunk &x, const Chunk &y) { return x.SL > y.SL; });
 }
 
-// split the chunks of the last partial "round" so that the tail of the ticket queue is made of short items
+// Tail refinement.  Tickets are handed out in list order (largest items first).  The items that
+// do not fill a whole "round" of `workers` warps would leave most warps idle for a full item time,
+// so that tail is cut into 2^k-times smaller items (k chosen by the cost model): the last warps
+// to finish then differ by one *small* item.
 static void refine_tail(std::vector<Chunk> &ch, int M, int workers, int pde, int n, long long tiles, int rt)
 {
     if (ch.empty()) return;
@@ -179,28 +182,31 @@ static void refine_tail(std::vector<Chunk> &ch, int M, int workers, int pde, int
         for (size_t i = 0; i < v.size(); ++i) t[i] = item_instr(pde, n, M, v[i].SL, 0, tiles, rt);
         return makespan(t, workers);
     };
-    double best = cost_of(ch);
-    for (int iter = 0; iter < 5; ++iter) {
-        const int bigSL = ch.front().SL;
-        if (bigSL <= 1) break;
-        size_t nbig = 0;
-        while (nbig < ch.size() && ch[nbig].SL == bigSL) ++nbig;
-        const size_t r = nbig % (size_t)workers;            // big items of the last partial round
-        if (r == 0) break;
-        std::vector<Chunk> v(ch.begin(), ch.begin() + (nbig - r));
-        std::vector<Chunk> rest(ch.begin() + nbig, ch.end());
-        for (size_t i = nbig - r; i < nbig; ++i) {           // halve
-            const Chunk &c = ch[i];
+    const size_t full = (ch.size() / (size_t)workers) * (size_t)workers;     // items in whole rounds keep their size
+    if (full == ch.size()) return;
+    std::vector<Chunk> head(ch.begin(), ch.begin() + full), tail(ch.begin() + full, ch.end());
+    std::vector<Chunk> best = ch;
+    double bestc = cost_of(ch);
+    for (int k = 1; k <= 5; ++k) {
+        std::vector<Chunk> nt;
+        bool changed = false;
+        for (const Chunk &c : tail) {
+            if (c.SL <= 1) { nt.push_back(c); continue; }
             const int half = c.SL / 2, cap = half * M;
             const int c1 = std::min(c.cnt, cap);
-            rest.push_back({c.g, c.s0, c1, half});
-            if (c.cnt > c1) rest.push_back({c.g, c.s0 + c1, c.cnt - c1, half});
+            nt.push_back({c.g, c.s0, c1, half});
+            if (c.cnt > c1) nt.push_back({c.g, c.s0 + c1, c.cnt - c1, half});
+            changed = true;
         }
-        std::stable_sort(rest.begin(), rest.end(), [](const Chunk &x, const Chunk &y) { return x.SL > y.SL; });
-        v.insert(v.end(), rest.begin(), rest.end());
-        const double cst = cost_of(v);
-        if (cst < best * 0.995) { best = cst; ch.swap(v); } else break;
+        if (!changed) break;
+        std::stable_sort(nt.begin(), nt.end(), [](const Chunk &x, const Chunk &y) { return x.SL > y.SL; });
+        tail.swap(nt);
+        std::vector<Chunk> v(head);
+        v.insert(v.end(), tail.begin(), tail.end());
+        const double c = cost_of(v);
+        if (c < bestc) { bestc = c; best.swap(v); }
     }
+    ch.swap(best);
 }
 
 static int make_plan(std::vector<ParamRow> &rows, int pde, int n, int n_sm, const long long *seg_rows, int nseg,
@@ -549,5 +555,43 @@ extern "C" int gptpinn_mlp_channels(const gptpinn_mlp *mlp, const float *xt_dev,
     for (int c = 0; c < 5; ++c) { o.ptr[c] = out_dev[c]; o.ld[c] = ld[c]; any = any || out_dev[c]; }
     if (!any) return GPTPINN_OK;
     CUDA_TRY(launch_mlp_channels(d, xt_dev, N, o, (cudaStream_t)stream));
+    return GPTPINN_OK;
+}
+
+// Host-only: the work-item plan the KG sweep would use on a device with `n_sm` SMs (no CUDA call).
+extern "C" int gptpinn_kg_plan(const double *grid_host, int Np, int n, int NR, int NI, int NB, int n_sm,
+                               const gptpinn_sweep_args *cfg, gptpinn_sweep_info *info, int sl_hist[6], int *covered)
+{
+    if (!grid_host || !info || !sl_hist || Np < 0 || n < 1 || n > kMaxN[PDE_KG] || n_sm < 1)
+        return fail(GPTPINN_E_INVALID, "gptpinn_kg_plan: bad arguments");
+    gptpinn_sweep_args a;
+    memset(&a, 0, sizeof(a));
+    if (cfg) { a.cfg_M = cfg->cfg_M; a.cfg_SL = cfg->cfg_SL; a.cfg_W = cfg->cfg_W; a.cfg_mode = cfg->cfg_mode; }
+    std::vector<ParamRow> rows((size_t)Np);
+    for (int i = 0; i < Np; ++i) {
+        rows[i].tp0 = (float)grid_host[3 * i]; rows[i].tp1 = (float)grid_host[3 * i + 1];
+        rows[i].sp0 = (float)grid_host[3 * i + 2]; rows[i].sp1 = (float)(2.0 * grid_host[3 * i + 2]); rows[i].idx = i;
+    }
+    long long seg[3] = {NR, NI, NB};
+    Plan plan;
+    int rc = make_plan(rows, PDE_KG, n, n_sm, seg, 3, &a, plan);
+    if (rc) return rc;
+    memset(info, 0, sizeof(*info));
+    info->M = plan.M; info->SL = plan.SL; info->W = plan.W; info->items = (int)plan.items.size(); info->groups = plan.groups;
+    info->ctas = plan.ctas; info->rounds = plan.rounds; info->priv = plan.priv;
+    for (int i = 0; i < 6; ++i) sl_hist[i] = 0;
+    std::vector<char> seen((size_t)Np, 0);
+    int cov = 0;
+    for (const ItemDesc &it : plan.items) {
+        int l = 0; while ((1 << l) < it.SL) ++l;
+        sl_hist[l]++;
+        if (it.sib_count > it.SL * plan.M) return fail(GPTPINN_E_INVALID, "plan: item overflows its lanes");
+        for (int s = 0; s < it.sib_count; ++s) {
+            const int idx = plan.sibs[it.sib_start + s].out_idx;
+            if (idx < 0 || idx >= Np || seen[idx]) return fail(GPTPINN_E_INVALID, "plan: parameter %d covered twice or out of range", idx);
+            seen[idx] = 1; ++cov;
+        }
+    }
+    if (covered) *covered = cov;
     return GPTPINN_OK;
 }

@@ -61,7 +61,7 @@ class Mlp(C.Structure):
 
 EXPORTS = ("gptpinn_version", "gptpinn_last_error", "gptpinn_create", "gptpinn_destroy",
            "gptpinn_kg_sweep", "gptpinn_b_sweep", "gptpinn_ac_sweep", "gptpinn_argmax_scan",
-           "gptpinn_mlp_channels", "gptpinn_ffma_peak")
+           "gptpinn_mlp_channels", "gptpinn_ffma_peak", "gptpinn_kg_plan")
 
 _lib = None
 
@@ -96,6 +96,9 @@ def lib():
     L.gptpinn_mlp_channels.restype = C.c_int
     L.gptpinn_ffma_peak.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_void_p]
     L.gptpinn_ffma_peak.restype = C.c_int
+    L.gptpinn_kg_plan.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.POINTER(SweepArgs), C.POINTER(SweepInfo), C.POINTER(C.c_int * 6), C.POINTER(C.c_int)]
+    L.gptpinn_kg_plan.restype = C.c_int
     _lib = L
     return L
 
@@ -119,3 +122,21 @@ def handle(device_index):
             check(lib().gptpinn_create(C.byref(hp)), "gptpinn_create")
         _handles[device_index] = h = hp
     return h
+
+
+def kg_plan(grid, n, NR=10000, NI=512, NB=1024, n_sm=148, cfg=None):
+    """Host-only view of the work-item plan (no GPU needed)."""
+    import numpy as np
+    grid = np.ascontiguousarray(np.asarray(grid, dtype=np.float64).reshape(-1, 3))
+    a = SweepArgs()
+    if cfg:
+        a.cfg_M, a.cfg_SL, a.cfg_W, a.cfg_mode = (int(cfg.get(k, 0)) for k in ("M", "SL", "W", "mode"))
+    info = SweepInfo()
+    hist = (C.c_int * 6)()
+    cov = C.c_int(0)
+    check(lib().gptpinn_kg_plan(grid.ctypes.data_as(C.POINTER(C.c_double)), grid.shape[0], n, NR, NI, NB, n_sm,
+                                C.byref(a), C.byref(info), C.byref(hist), C.byref(cov)), "gptpinn_kg_plan")
+    d = info.asdict()
+    d["sl_hist"] = {1 << i: hist[i] for i in range(6) if hist[i]}
+    d["covered"] = cov.value
+    return d

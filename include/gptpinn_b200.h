@@ -171,6 +171,12 @@ typedef struct {
 int  gptpinn_mlp_channels(const gptpinn_mlp *mlp, const float *xt_dev, long long N,
                           float *const out_dev[5], const long long ld[5], void *stream);
 
+/* Host-only (no CUDA call): the work-item plan gptpinn_kg_sweep would build for this grid on a device
+ * with n_sm SMs.  sl_hist[l] = number of items with 2^l sibling lanes; *covered = parameters assigned
+ * (must equal Np).  Used by tests and for tuning; no reference counterpart.                            */
+int  gptpinn_kg_plan(const double *grid_host, int Np, int n, int NR, int NI, int NB, int n_sm,
+                     const gptpinn_sweep_args *cfg, gptpinn_sweep_info *info, int sl_hist[6], int *covered);
+
 /* FFMA-only microbenchmark on the current device: best-of-`reps` FP32 CUDA-core throughput in
  * TFLOP/s (2 flop per FMA).  It is the measured denominator of the sweep kernel's roofline;
  * it has no counterpart in the reference.  Synchronises the stream.                            */
