@@ -379,7 +379,7 @@ static int run_sweep(gptpinn_handle *h, int pde, int n, const Segments &seg, Pac
 
     p.packed = h->packed;
     p.tiles_per_pass = (int)tiles;
-    p.nR = (float)NR; p.nI = (float)NI; p.nB = (float)NB;
+    p.invR = (float)(1.0 / NR); p.invI = (float)(1.0 / NI); p.invB = (float)(1.0 / NB);
     p.fac1 = (float)(2.0 / NR); p.fac2 = (float)(2.0 / NB); p.fac3 = (float)(2.0 / NI);
     p.lr = (float)a->lr;
     p.epochs = a->epochs;

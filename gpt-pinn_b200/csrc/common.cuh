@@ -63,7 +63,7 @@ struct SweepParams {
     const float   *packed;           // tile stream
     int            ntile[MAX_SEG];   // tiles per segment
     int            tiles_per_pass;
-    float          nR, nI, nB;       // sizes as float (loss means)
+    float          invR, invI, invB; // 1/N_R, 1/N_IC, 1/N_BC as fp32 (loss = sum of per-segment means)
     float          fac1, fac2, fac3; // (float)(2/NR), (float)(2/NB), (float)(2/NI)
     float          lr;
     int            epochs, rec_every, nrec;

@@ -25,6 +25,12 @@
 //           the current row retire (software pipelining; no extra registers).
 #pragma once
 #include "common.cuh"
+#ifndef GP_FWD_VARIANT
+#define GP_FWD_VARIANT 0
+#endif
+#ifndef GP_PHASE_SYNC
+#define GP_PHASE_SYNC 0
+#endif
 
 namespace gp {
 
@@ -160,29 +166,30 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
         const int sl = lane & (SL - 1), slice = lane / SL;
 
         float c[M][N], g[M][N];
-        float sp0[M], sp1[M], mn[M], lastloss[M];
-        int oidx[M];
+        float sp0[M], sp1[M], mn[M];
 #pragma unroll
         for (int m = 0; m < M; ++m) {
             const int s = sl * M + m;
             const bool valid = active && s < it.sib_count;
-            sp0[m] = 0.f; sp1[m] = 0.f; oidx[m] = -1;
+            sp0[m] = 0.f; sp1[m] = 0.f;
+            int oi = 0;
             if (valid) {
                 const SibDesc sd = p.sibs[it.sib_start + s];
-                sp0[m] = sd.sp0; sp1[m] = sd.sp1; oidx[m] = sd.out_idx;
+                sp0[m] = sd.sp0; sp1[m] = sd.sp1; oi = sd.out_idx;
             }
 #pragma unroll
             for (int k = 0; k < N; ++k)
-                c[m][k] = valid ? (p.c0_per_param ? p.c0[(size_t)oidx[m] * N + k] : p.c0[k]) : 0.f;
+                c[m][k] = valid ? (p.c0_per_param ? p.c0[(size_t)oi * N + k] : p.c0[k]) : 0.f;
             mn[m] = __int_as_float(0x7f800000);
-            lastloss[m] = 0.f;
         }
 
         for (int j = 0; j <= p.epochs; ++j) {
-            float lA[M], lB[M], lC[M], lD[M];      // per-segment squared-residual sums
+            // lacc: squared residuals of the current segment (this lane's rows); lsum: segments already
+            // folded in, each scaled by 1/rows of its segment (the loss is a sum of per-segment means)
+            float lacc[M], lsum[M];
 #pragma unroll
             for (int m = 0; m < M; ++m) {
-                lA[m] = lB[m] = lC[m] = lD[m] = 0.f;
+                lacc[m] = 0.f; lsum[m] = 0.f;
 #pragma unroll
                 for (int k = 0; k < N; ++k) g[m][k] = 0.f;
             }
@@ -244,7 +251,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                                 const float ux = dotn<N>(Xv, c[m], 0.f);
                                 const float t1 = dotn<N>(Tv, c[m], Tv[N]);
                                 const float d = fmaf(u, ux, t1);
-                                lA[m] = fmaf(d, d, lA[m]);
+                                lacc[m] = fmaf(d, d, lacc[m]);
                                 first[m] = has_fhat ? d + fh : d;
                                 wx[m] = first[m] * u; wp[m] = first[m] * ux;
                             }
@@ -270,18 +277,28 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                         for (; r < RT; r += RL) {
                             const int rn = min(r + RL, RT - 1);
                             float first[M], w2[M];
+                            // The T contraction is seeded with the nonlinear term, d = ((g*u^2 + forcing) + T.c), so it
+                            // depends on the finished P contraction: the compiler then schedules the M independent
+                            // P chains together (P[k] stays in the operand-reuse cache across the M parameters) and the
+                            // M T chains together, instead of pairing u/t FFMAs that both fetch c, P[k] and T[k] from
+                            // the register file (3 register-file reads = a 2-cycle dispatch on this part).
+                            float uu[M];
+#pragma unroll
+                            for (int m = 0; m < M; ++m) uu[m] = dotn<N>(Pv, c[m], 0.f);
 #pragma unroll
                             for (int m = 0; m < M; ++m) {
-                                const float u = dotn<N>(Pv, c[m], 0.f);
-                                const float t1 = dotn<N>(Tv, c[m], Tv[N]);
+                                const float u = uu[m];
                                 float d, nl;
-                                if constexpr (PDE == PDE_KG) { d = fmaf(sp0[m], u * u, t1); nl = sp1[m] * u; }          // g*u^2 ; 2g*u
-                                else { const float u2 = u * u; d = fmaf(sp0[m], u2 * u, t1); nl = sp1[m] * u2; }       // e*u^3 ; 3e*u^2
-                                lA[m] = fmaf(d, d, lA[m]);
+                                if constexpr (PDE == PDE_KG) { d = dotn<N>(Tv, c[m], fmaf(sp0[m], u * u, Tv[N])); nl = sp1[m] * u; }            // g*u^2 ; 2g*u
+                                else { const float u2 = u * u; d = dotn<N>(Tv, c[m], fmaf(sp0[m], u2 * u, Tv[N])); nl = sp1[m] * u2; }         // e*u^3 ; 3e*u^2
+                                lacc[m] = fmaf(d, d, lacc[m]);
                                 first[m] = has_fhat ? d + fh : d;          // the update ignores fhat (N3)
                                 w2[m] = first[m] * nl;
                             }
                             if (has_fhat) fh = slot[fhoff + rn];
+#if GP_PHASE_SYNC
+                            __syncwarp();          // scheduling fence: keeps the forward contractions of all M parameters together
+#endif
 #pragma unroll
                             for (int q = 0; q < NQT; ++q) {
 #pragma unroll
@@ -303,9 +320,11 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                 release();
             }
 #pragma unroll
-            for (int m = 0; m < M; ++m)
+            for (int m = 0; m < M; ++m) {
+                lsum[m] = lacc[m] * p.invR; lacc[m] = 0.f;
 #pragma unroll
                 for (int k = 0; k < N; ++k) g[m][k] *= fac1;
+            }
 
             // ------------------------------ segment 1: initial-condition rows -------------
             for (int t = 0; t < p.ntile[1]; ++t) {
@@ -324,8 +343,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                                 const float d1 = dotn<N>(Av, c[m], 0.f) - tg;
                                 const float d2 = dotn<N>(Bv, c[m], 0.f);
                                 const float e2 = d2 - tg2;
-                                lB[m] = fmaf(d1, d1, lB[m]);
-                                lC[m] = fmaf(e2, e2, lC[m]);
+                                lacc[m] = fmaf(d1, d1, lacc[m]);
+                                lacc[m] = fmaf(e2, e2, lacc[m]);
                                 const float w1 = fac3 * d1, w2 = fac3 * d2;
 #pragma unroll
                                 for (int k = 0; k < N; ++k) {
@@ -337,7 +356,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
 #pragma unroll
                             for (int m = 0; m < M; ++m) {
                                 const float d1 = dotn<N>(Av, c[m], 0.f) - tg;
-                                lB[m] = fmaf(d1, d1, lB[m]);
+                                lacc[m] = fmaf(d1, d1, lacc[m]);
                                 const float w1 = fac3 * d1;
 #pragma unroll
                                 for (int k = 0; k < N; ++k) g[m][k] = fmaf(w1, Av[k], g[m][k]);
@@ -347,6 +366,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                 }
                 release();
             }
+
+#pragma unroll
+            for (int m = 0; m < M; ++m) { lsum[m] = fmaf(lacc[m], p.invI, lsum[m]); lacc[m] = 0.f; }
 
             // ------------------------------ segment 2 (3): boundary rows ------------------
             for (int seg = 2; seg < TR::NSEG; ++seg) {
@@ -363,7 +385,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
 #pragma unroll
                                 for (int m = 0; m < M; ++m) {
                                     const float d = dotn<N>(Av, c[m], 0.f) - dotn<N>(Bv, c[m], 0.f);
-                                    if (seg == 2) lC[m] = fmaf(d, d, lC[m]); else lD[m] = fmaf(d, d, lD[m]);
+                                    lacc[m] = fmaf(d, d, lacc[m]);
                                     const float w = fac2 * d;
 #pragma unroll
                                     for (int k = 0; k < N; ++k) g[m][k] = fmaf(w, Dv[k], g[m][k]);
@@ -375,8 +397,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                                     const float dv = dotn<N>(Av, c[m], 0.f);
                                     const float e = dv - tg;
                                     float w;
-                                    if constexpr (PDE == PDE_KG) { lD[m] = fmaf(e, e, lD[m]); w = fac2 * e; }
-                                    else { lC[m] = fmaf(e, e, lC[m]); w = fac2 * dv; }   // Burgers: BC_u absent from update (N3)
+                                    lacc[m] = fmaf(e, e, lacc[m]);
+                                    if constexpr (PDE == PDE_KG) w = fac2 * e;
+                                    else w = fac2 * dv;                                 // Burgers: BC_u absent from update (N3)
 #pragma unroll
                                     for (int k = 0; k < N; ++k) g[m][k] = fmaf(w, Av[k], g[m][k]);
                                 }
@@ -388,52 +411,40 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
             }
 
             // ------------------------------ end of pass: reduce, loss, update -------------
+#pragma unroll
+            for (int m = 0; m < M; ++m) lsum[m] = fmaf(lacc[m], p.invB, lsum[m]);       // all boundary segments share 1/N_BC
             for (int off = SL; off < 32; off <<= 1) {
 #pragma unroll
                 for (int m = 0; m < M; ++m) {
-                    lA[m] += __shfl_xor_sync(FULLM, lA[m], off);
-                    lB[m] += __shfl_xor_sync(FULLM, lB[m], off);
-                    lC[m] += __shfl_xor_sync(FULLM, lC[m], off);
-                    lD[m] += __shfl_xor_sync(FULLM, lD[m], off);
+                    lsum[m] += __shfl_xor_sync(FULLM, lsum[m], off);
 #pragma unroll
                     for (int k = 0; k < N; ++k) g[m][k] += __shfl_xor_sync(FULLM, g[m][k], off);
                 }
             }
+            const bool rec = p.trace != nullptr && p.rec_every > 0 && (j % p.rec_every) == 0;
+            const bool last = (j == p.epochs);
 #pragma unroll
             for (int m = 0; m < M; ++m) {
-                float loss;
-                if constexpr (PDE == PDE_KG)        // ((R + IC1) + IC2) + BC      KG_models.py:45-50
-                    loss = __fadd_rn(__fadd_rn(__fadd_rn(__fdiv_rn(lA[m], p.nR), __fdiv_rn(lB[m], p.nI)),
-                                               __fdiv_rn(lC[m], p.nI)), __fdiv_rn(lD[m], p.nB));
-                else if constexpr (PDE == PDE_B)    // (R + IC) + BC               B_models.py:42-46
-                    loss = __fadd_rn(__fadd_rn(__fdiv_rn(lA[m], p.nR), __fdiv_rn(lB[m], p.nI)), __fdiv_rn(lC[m], p.nB));
-                else                                // ((R + IC) + BC) + BCx       AC_models.py:49-54
-                    loss = __fadd_rn(__fadd_rn(__fadd_rn(__fdiv_rn(lA[m], p.nR), __fdiv_rn(lB[m], p.nI)),
-                                               __fdiv_rn(lC[m], p.nB)), __fdiv_rn(lD[m], p.nB));
-                lastloss[m] = loss;
-                if (p.trace != nullptr && p.rec_every > 0 && (j % p.rec_every) == 0 && slice == 0 && oidx[m] >= 0)
-                    p.trace[(size_t)oidx[m] * p.nrec + j / p.rec_every] = loss;
-                if (j < p.epochs) {
+                const float loss = lsum[m];       // = mean_R + mean_IC(s) + mean_BC(s)   (KG_models.py:45-50, B_models.py:42-46, AC_models.py:49-54)
+                if ((rec || last) && slice == 0 && (sl * M + m) < it.sib_count) {
+                    const int oi = p.sibs[it.sib_start + sl * M + m].out_idx;
+                    if (rec) p.trace[(size_t)oi * p.nrec + j / p.rec_every] = loss;
+                    if (last) {
+                        p.f_out[oi] = loss;
+                        p.m_out[oi] = mn[m];
+                        if (p.c_out != nullptr) {
+#pragma unroll
+                            for (int k = 0; k < N; ++k) p.c_out[(size_t)oi * N + k] = c[m][k];
+                        }
+                    }
+                }
+                if (!last) {
                     if (loss < mn[m]) mn[m] = loss;
 #pragma unroll
                     for (int k = 0; k < N; ++k) c[m][k] = __fsub_rn(c[m][k], __fmul_rn(p.lr, g[m][k]));
                 }
             }
         }   // epochs
-
-        if (slice == 0) {
-#pragma unroll
-            for (int m = 0; m < M; ++m) {
-                if (oidx[m] >= 0) {
-                    p.f_out[oidx[m]] = lastloss[m];
-                    p.m_out[oidx[m]] = mn[m];
-                    if (p.c_out != nullptr) {
-#pragma unroll
-                        for (int k = 0; k < N; ++k) p.c_out[(size_t)oidx[m] * N + k] = c[m][k];
-                    }
-                }
-            }
-        }
     }   // items
 
     if (PRIV) {     // drain: NST tiles are always in flight; no bulk copy may outlive the CTA

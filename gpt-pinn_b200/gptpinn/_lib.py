@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgptpinn_b200.so")
+LIB_PATH = os.environ.get("GPTPINN_LIB") or os.path.join(_HERE, "lib", "libgptpinn_b200.so")   # env override: kernel-variant experiments only
 
 _fp = C.POINTER(C.c_float)
 
