@@ -125,11 +125,21 @@ static double item_instr(int pde, int n, int M, int SL, long long rows_total, lo
 {
     const int RL = 32 / SL;
     const double rows_lane = (double)tiles * ((rt + RL - 1) / RL);     // every tile costs whole lane-rows
-    const double build = (double)tiles * (28.0 * (n / 4 + 1) * rt / 32.0 + 40.0);
+    const double build = (double)tiles * (36.0 * (n / 4 + 1) * rt / 32.0 + 90.0);   // T block + ring bookkeeping per tile
     (void)rows_total;
-    return rows_lane * per_row_instr(pde, n, M) + build;
+    // measured issue efficiency relative to M = 5 (KG n = 15 single-round runs: 0.595 / 0.526 / 0.453 / 0.304 of FP32 peak)
+    const double rel = M >= 5 ? 1.0 : (M == 4 ? 0.895 : (M >= 2 ? 0.835 : 0.624));
+    return (rows_lane * per_row_instr(pde, n, M) + build) / rel;
 }
-static const double kL2BytesPerCycle = 4000.0;       // chip-wide L2 -> SM budget the planner allows itself
+// measured issue efficiency of one SMSP vs resident warps (B200, KG n=15: 1 warp 0.49/0.60, 2 warps 1.0 relative)
+static double smsp_eff(double warps_per_smsp)
+{
+    if (warps_per_smsp <= 1.0) return 0.58;
+    if (warps_per_smsp <= 2.0) return 0.58 + 0.15 * (warps_per_smsp - 1.0);
+    if (warps_per_smsp <= 4.0) return 0.73 + 0.06 * (warps_per_smsp - 2.0);
+    return 0.85;
+}
+static const double kL2BytesPerCycle = 2200.0;       // chip-wide L2 -> SM budget the planner allows itself
 
 // makespan of `t` (already in hand-out order) on `workers` identical workers, greedy (= ticket order)
 static double makespan(const std::vector<double> &t, int workers)
@@ -151,7 +161,7 @@ static double makespan(const std::vector<double> &t, int workers)
 struct Chunk { int g, s0, cnt, SL; };     // siblings [s0, s0+cnt) of group g on SL sibling-lanes
 
 // binary decomposition of every group into power-of-two lane counts, largest first
-static void decompose(const std::vector<int> &gstart, int M, std::vector<Chunk> &out)
+static void decompose(const std::vector<int> &gstart, int M, int sl_cap, std::vector<Chunk> &out)
 {
     out.clear();
     const int ngroups = (int)gstart.size() - 1;
@@ -159,9 +169,9 @@ static void decompose(const std::vector<int> &gstart, int M, std::vector<Chunk> 
         int S = gstart[g + 1] - gstart[g], s0 = 0;
         while (S > 0) {
             int lanes = (S + M - 1) / M;                 // sibling lanes still needed
-            int SL = 32;
-            while (SL > lanes) SL >>= 1;                 // largest power of two <= lanes
-            if (SL < lanes && SL * 2 <= 32 && (long long)SL * 2 * M - S < M) SL *= 2;   // a last partial lane
+            int SL = sl_cap;
+            while (SL > lanes) SL >>= 1;                 // largest power of two <= lanes (and <= cap)
+            if (SL < lanes && SL * 2 <= sl_cap && (long long)SL * 2 * M - S < M) SL *= 2;   // a last partial lane
             const int cnt = std::min(S, SL * M);
             out.push_back({g, s0, cnt, SL});
             s0 += cnt; S -= cnt;
@@ -243,24 +253,32 @@ static int make_plan(std::vector<ParamRow> &rows, int pde, int n, int n_sm, cons
         if (mode != 1) {
             const int wsmem = (int)((227.0 * 1024 - 64) / (NST_PRIV * slot_p + (n / 4 + 1) * 4 * RT_PRIV * 4 + NST_PRIV * 8));
             const int maxwp = std::max(1, std::min(maxw, wsmem));
-            const int W = a->cfg_W > 0 ? std::min(a->cfg_W, maxwp) : maxwp;
-            const int workers = n_sm * W;
-            if (a->cfg_SL > 0) {
-                ch.clear();
-                for (int g = 0; g < plan.groups; ++g)
-                    for (int s0 = 0, S = gstart[g + 1] - gstart[g]; s0 < S; s0 += a->cfg_SL * M)
-                        ch.push_back({g, s0, std::min(S - s0, a->cfg_SL * M), a->cfg_SL});
-            } else {
-                decompose(gstart, M, ch);
-                refine_tail(ch, M, workers, pde, n, tiles_p, RT_PRIV);
+            for (int W = maxwp; W >= 1; --W) {
+                if (a->cfg_W > 0 && W != std::min(a->cfg_W, maxwp)) continue;
+                if (a->cfg_W == 0 && W < maxwp - 3) break;                 // fewer resident warps never paid off in practice
+                const int workers = n_sm * W;
+                for (int cap = 32; cap >= 1; cap >>= 1) {
+                    if (a->cfg_SL > 0) {
+                        if (cap != 32) break;
+                        ch.clear();
+                        for (int g = 0; g < plan.groups; ++g)
+                            for (int s0 = 0, S = gstart[g + 1] - gstart[g]; s0 < S; s0 += a->cfg_SL * M)
+                                ch.push_back({g, s0, std::min(S - s0, a->cfg_SL * M), a->cfg_SL});
+                    } else {
+                        decompose(gstart, M, cap, ch);
+                        if (cap < 32 && !ch.empty() && ch.front().SL < cap) break;     // the cap no longer binds
+                        refine_tail(ch, M, workers, pde, n, tiles_p, RT_PRIV);
+                    }
+                    std::vector<double> t(ch.size());
+                    for (size_t i = 0; i < ch.size(); ++i) t[i] = item_instr(pde, n, M, ch[i].SL, 0, tiles_p, RT_PRIV);
+                    const int Wuse = (int)std::max<long long>(1, std::min<long long>(W, ((long long)ch.size() + n_sm - 1) / n_sm));
+                    const double wps = Wuse / 4.0;
+                    const double issue = makespan(t, n_sm * Wuse) * std::max(1.0, std::ceil(wps)) / smsp_eff(std::max(1.0, wps));
+                    const double l2 = (double)ch.size() * tiles_p * slot_p / kL2BytesPerCycle;
+                    const double cst = std::max(issue, l2);
+                    if (cst < best) { best = cst; bM = M; bSL = ch.empty() ? 1 : ch.front().SL; bW = Wuse; bPriv = 1; bestChunks = ch; }
+                }
             }
-            std::vector<double> t(ch.size());
-            for (size_t i = 0; i < ch.size(); ++i) t[i] = item_instr(pde, n, M, ch[i].SL, 0, tiles_p, RT_PRIV);
-            const double wps = std::ceil(std::min<double>(W, (double)ch.size() / n_sm + 0.999) / 4.0);   // warps sharing an SMSP
-            const double issue = makespan(t, workers) * std::max(1.0, wps);
-            const double l2 = (double)ch.size() * tiles_p * slot_p / kL2BytesPerCycle;
-            const double cst = std::max(issue, l2);
-            if (cst < best) { best = cst; bM = M; bSL = ch.empty() ? 1 : ch.front().SL; bW = W; bPriv = 1; bestChunks = ch; }
         }
         // ---- shared ring: static rounds, uniform item size ----
         if (mode != 2) {
@@ -272,7 +290,7 @@ static int make_plan(std::vector<ParamRow> &rows, int pde, int n, int n_sm, cons
                     if (a->cfg_W > 0 && W != std::min(a->cfg_W, maxw)) continue;
                     const long long ctas = std::min<long long>(n_sm, (nit + W - 1) / W);
                     const double rounds = (double)((nit + ctas * W - 1) / (ctas * W));
-                    const double issue = rounds * std::ceil(W / 4.0) * item_instr(pde, n, M, SL, 0, tiles_s, RT_SHARED);
+                    const double issue = 1.2 * rounds * std::ceil(W / 4.0) * item_instr(pde, n, M, SL, 0, tiles_s, RT_SHARED) / smsp_eff(W / 4.0);
                     const double l2 = rounds * ctas * tiles_s * slot_s / kL2BytesPerCycle;
                     const double cst = std::max(issue, l2) * 1.02;          // ties go to the private rings
                     if (cst < best) { best = cst; bM = M; bSL = SL; bW = W; bPriv = 0; }
