@@ -12,6 +12,7 @@
 #include "../../include/gptpinn_b200.h"
 #include "pack.cuh"
 #include "precomp.cuh"
+#include "pinn_train.cuh"
 #include "sweep_kernel.cuh"
 
 namespace gp {
@@ -51,6 +52,7 @@ struct gptpinn_handle {
     void *items = nullptr;     size_t items_cap = 0;      // bytes
     void *sibs = nullptr;      size_t sibs_cap = 0;       // bytes
     unsigned int *counter = nullptr;                      // work-item ticket
+    void *train_ws = nullptr;  size_t train_cap = 0;      // packed params | adam m | adam v | partials | status | stop
 };
 
 static int ensure(void **ptr, size_t *cap, size_t need)
@@ -92,6 +94,7 @@ extern "C" int gptpinn_destroy(gptpinn_handle *h)
     if (h->items) cudaFree(h->items);
     if (h->sibs) cudaFree(h->sibs);
     if (h->counter) cudaFree(h->counter);
+    if (h->train_ws) cudaFree(h->train_ws);
     delete h;
     return GPTPINN_OK;
 }
@@ -611,5 +614,83 @@ extern "C" int gptpinn_kg_plan(const double *grid_host, int Np, int n, int NR, i
         }
     }
     if (covered) *covered = cov;
+    return GPTPINN_OK;
+}
+
+extern "C" int gptpinn_pinn_train(gptpinn_handle *h, const gptpinn_pinn_problem *q, const gptpinn_mlp *net,
+                                  const gptpinn_train_args *ta, float *status_dev, void *stream)
+{
+    if (!h || !q || !net || !ta || !status_dev) return fail(GPTPINN_E_INVALID, "gptpinn_pinn_train: NULL argument");
+    if (q->pde != GPTPINN_PDE_KG && q->pde != GPTPINN_PDE_BURGERS) return fail(GPTPINN_E_INVALID, "pde must be KG (0) or Burgers (1)");
+    if (net->nlayers < 3 || net->nlayers > PINN_MAX_HIDDEN + 2) return fail(GPTPINN_E_UNSUPPORTED, "nlayers = %d outside 3..%d", net->nlayers, PINN_MAX_HIDDEN + 2);
+    if (net->layers[0] != 2 || net->layers[net->nlayers - 1] != 1) return fail(GPTPINN_E_INVALID, "network must map 2 inputs to 1 output");
+    if (q->NR < 1 || q->NI < 1 || q->NB < 1) return fail(GPTPINN_E_INVALID, "NR, NI, NB must be >= 1");
+    if (!q->xt_resid || !q->IC_xt || !q->IC_u1 || !q->BC_xt || !q->BC_u) return fail(GPTPINN_E_INVALID, "point sets and targets are required");
+    if (q->pde == GPTPINN_PDE_KG && !q->xcos) return fail(GPTPINN_E_INVALID, "xcos is required for Klein-Gordon");
+    if (ta->epochs < 0) return fail(GPTPINN_E_INVALID, "epochs < 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = -1;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != h->device) return fail(GPTPINN_E_INVALID, "handle belongs to device %d, current device is %d", h->device, dev);
+    int coop = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    if (!coop) return fail(GPTPINN_E_UNSUPPORTED, "device does not support cooperative launch");
+
+    PinnDesc d;
+    memset(&d, 0, sizeof(d));
+    d.nlayers = net->nlayers; d.act = net->act; d.pde = q->pde;
+    int P = 0;
+    for (int l = 0; l < net->nlayers; ++l) {
+        d.layers[l] = net->layers[l];
+        if (d.layers[l] < 1 || d.layers[l] > 40) return fail(GPTPINN_E_UNSUPPORTED, "layer width %d outside 1..40", d.layers[l]);
+    }
+    for (int l = 0; l < net->nlayers - 1; ++l) {
+        if (!net->W[l] || !net->b[l]) return fail(GPTPINN_E_INVALID, "W[%d] or b[%d] is NULL", l, l);
+        P += d.layers[l] * d.layers[l + 1] + d.layers[l + 1];
+    }
+    d.n_params = P;
+    if (q->pde == GPTPINN_PDE_KG) { d.pa = (float)q->p0; d.pb = (float)q->p1; d.pc = (float)q->p2; }
+    else { d.pa = (float)(-q->p0); d.pb = 0.f; d.pc = 0.f; }
+    d.NR = q->NR; d.NI = q->NI; d.NB = q->NB;
+    d.xt_resid = q->xt_resid; d.IC_xt = q->IC_xt; d.BC_xt = q->BC_xt; d.f_hat = q->f_hat; d.xcos = q->xcos;
+    d.IC_u1 = q->IC_u1; d.IC_u2 = q->IC_u2; d.BC_u = q->BC_u;
+    d.invR = (float)(1.0 / q->NR); d.invI = (float)(1.0 / q->NI); d.invB = (float)(1.0 / q->NB);
+    d.epochs = ta->epochs;
+    d.lr = (float)ta->lr; d.beta1 = (float)ta->beta1; d.beta2 = (float)ta->beta2;
+    d.omb1 = (float)(1.0 - ta->beta1); d.omb2 = (float)(1.0 - ta->beta2); d.eps = (float)ta->eps;
+    d.tol = ta->tol >= 0 ? (float)ta->tol : -1.f;
+    d.loss_trace = ta->trace_every > 0 ? ta->loss_trace_dev : nullptr;
+    d.trace_every = ta->trace_every;
+    d.grad_out = ta->grad_out_dev;
+
+    int blocks = 0, n_partials = 0;
+    size_t smem = 0;
+    CUDA_TRY(plan_pinn_train(d, h->n_sm, &blocks, &smem, &n_partials));
+    const int stride = (P + 4 + 31) & ~31;
+    const size_t need = ((size_t)3 * P + (size_t)n_partials * stride + 64) * sizeof(float);
+    int rc = ensure(&h->train_ws, &h->train_cap, need);
+    if (rc) return rc;
+    float *ws = (float *)h->train_ws;
+    d.params = ws; d.adam_m = ws + P; d.adam_v = ws + 2 * P;
+    d.partials = ws + 3 * P; d.n_partials = n_partials; d.partial_stride = stride;
+    float *tail = d.partials + (size_t)n_partials * stride;
+    d.stop = (int *)tail;
+    d.status = status_dev;
+    CUDA_TRY(cudaMemsetAsync(ws + P, 0, (size_t)2 * P * sizeof(float), st));            // fresh optimizer state
+    CUDA_TRY(cudaMemsetAsync(tail, 0, 64 * sizeof(float), st));
+    CUDA_TRY(cudaMemsetAsync(status_dev, 0, 2 * sizeof(float), st));
+    int off = 0;
+    for (int l = 0; l < net->nlayers - 1; ++l) {                                        // pack: W then b, layer after layer
+        const int nw = d.layers[l] * d.layers[l + 1], nb = d.layers[l + 1];
+        CUDA_TRY(cudaMemcpyAsync(ws + off, net->W[l], nw * sizeof(float), cudaMemcpyDeviceToDevice, st)); off += nw;
+        CUDA_TRY(cudaMemcpyAsync(ws + off, net->b[l], nb * sizeof(float), cudaMemcpyDeviceToDevice, st)); off += nb;
+    }
+    if (ta->epochs > 0) CUDA_TRY(launch_pinn_train(d, blocks, smem, st));
+    off = 0;
+    for (int l = 0; l < net->nlayers - 1; ++l) {                                        // unpack into the caller's tensors
+        const int nw = d.layers[l] * d.layers[l + 1], nb = d.layers[l + 1];
+        CUDA_TRY(cudaMemcpyAsync((void *)net->W[l], ws + off, nw * sizeof(float), cudaMemcpyDeviceToDevice, st)); off += nw;
+        CUDA_TRY(cudaMemcpyAsync((void *)net->b[l], ws + off, nb * sizeof(float), cudaMemcpyDeviceToDevice, st)); off += nb;
+    }
     return GPTPINN_OK;
 }

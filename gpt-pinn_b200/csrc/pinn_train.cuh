@@ -1,0 +1,36 @@
+// pinn_train.cuh -- descriptor of the fused full-PINN training kernel (pinn_train.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace gp {
+
+constexpr int PINN_MAX_HIDDEN = 6;            // hidden layers (KG: 2, Burgers: 4)
+
+struct PinnDesc {
+    int nlayers;                              // entries of layers[] (inputs, hidden..., output)
+    int layers[PINN_MAX_HIDDEN + 2];
+    int act;                                  // 0 cos, 1 tanh
+    int pde;                                  // 0 Klein-Gordon, 1 Burgers
+    float pa, pb, pc;                         // KG: alpha, beta, gamma      Burgers: -nu, 0, 0
+    int n_params;                             // total weights + biases
+    float *params;                            // device [n_params]: per layer W (row-major [out][in]) then b; updated in place
+    float *adam_m, *adam_v;                   // device [n_params]
+    float *grad_out;                          // device [n_params] or nullptr: gradient of the last executed step
+    int NR, NI, NB;
+    const float *xt_resid, *IC_xt, *BC_xt;    // [N,2]
+    const float *f_hat, *xcos;                // [NR] (f_hat may be null; xcos KG only)
+    const float *IC_u1, *IC_u2, *BC_u;        // [NI], [NI] (KG only, may be null), [NB]
+    float invR, invI, invB;
+    int epochs;
+    float lr, beta1, beta2, omb1, omb2, eps;  // omb = (float)(1 - beta) as torch forms it in double
+    float tol;                                // < 0: no tolerance stop
+    float *partials; int n_partials; int partial_stride;   // [n_partials][partial_stride >= n_params + 4]
+    float *status;                            // [2]: last evaluated loss, epochs executed (as int bits)
+    int *stop;                                // [1]
+    float *loss_trace; int trace_every;       // optional: loss before the step of epochs 1, 1+k, ...
+};
+
+cudaError_t plan_pinn_train(const PinnDesc &d, int n_sm, int *blocks, size_t *smem, int *n_partials);
+cudaError_t launch_pinn_train(const PinnDesc &d, int blocks, size_t smem, cudaStream_t st);
+
+}  // namespace gp

@@ -57,6 +57,6 @@ def offline_generation(nu_train, xt_size, IC_size, BC_size, IC_u, BC_u, out,
 
 def pinn_train(PINN, nu, xt_resid, IC_xt, IC_u, BC_xt, BC_u, f_hat,
                epochs_pinn, lr_pinn, tol):
-    loss = pinn.train_adam(PINN, lambda: PINN.loss(xt_resid, IC_xt, IC_u, BC_xt, BC_u, f_hat),
-                           epochs_pinn, lr_pinn, tol=tol)
-    print(f"PINN Final Loss: {loss}")
+    r = pinn.train_fused(PINN, "burgers", (nu,), xt_resid, f_hat, IC_xt, IC_u, None, BC_xt, BC_u,
+                         epochs_pinn, lr_pinn, tol=tol)
+    print(f"PINN Final Loss: {r['loss'].item()}")

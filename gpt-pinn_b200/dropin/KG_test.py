@@ -54,8 +54,8 @@ def pinn_test(kg_test, layers_pinn, xcos_x2cos2, xt_resid, IC_xt, IC_u1, IC_u2,
     for i, (alpha, beta, gamma) in enumerate(kg_test):
         t_start = time.time()
         PINN = NN(layers_pinn, alpha, beta, gamma, xcos_x2cos2).to(device)
-        pinn.train_adam(PINN, lambda: PINN.loss(xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u),
-                        epochs_pinn, lr_pinn)
+        pinn.train_fused(PINN, "kg", (alpha, beta, gamma), xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u,
+                         epochs_pinn, lr_pinn, xcos=xcos_x2cos2)
         with torch.no_grad():
             soln = PINN(xt_test)
         dt = (time.time() - t_start) / 3600
@@ -69,9 +69,12 @@ def pinn_test_loss(kg_test, layers_pinn, xcos_x2cos2, xt_resid, IC_xt, IC_u1,
     losses = np.zeros((101, len(kg_test)))
     for i, (alpha, beta, gamma) in enumerate(kg_test):
         PINN = NN(layers_pinn, alpha, beta, gamma, xcos_x2cos2).to(device)
-        loss_fn = lambda: PINN.loss(xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u)  # noqa: E731
-        losses[0, i] = loss_fn().item()
-        rec = pinn.train_adam(PINN, loss_fn, epochs_pinn, lr_pinn, record_every=1000)
-        for j, v in rec.items():
-            losses[int(j / 1000), i] = v
+        # loss before the step of epochs 1, 1001, 2001, ... == loss after 0, 1000, 2000, ... steps (KG_test.py:125-139)
+        r = pinn.train_fused(PINN, "kg", (alpha, beta, gamma), xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u,
+                             epochs_pinn, lr_pinn, xcos=xcos_x2cos2, trace_every=1000)
+        tr = r["trace"].cpu().numpy()
+        losses[:min(101, len(tr)), i] = tr[:101]
+        with torch.enable_grad():
+            final = PINN.loss(xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u).item()
+        losses[int(epochs_pinn / 1000), i] = final
     return losses

@@ -2,7 +2,8 @@
 
 offline_generation: reference KG_train.py:8-43 -- one fused CUDA launch trains c for every grid
 parameter, then the exact arg-max scan picks (largest_loss, largest_case).
-pinn_train: reference KG_train.py:48-59 -- 75 000 Adam steps on the full PINN.
+pinn_train: reference KG_train.py:48-59 -- 75 000 Adam steps on the full PINN, all inside one persistent
+cooperative CUDA kernel (gptpinn_pinn_train).
 """
 import numpy as np
 import torch
@@ -31,6 +32,6 @@ def offline_generation(kg_train, c_initial, xt_size, IC_size, BC_size, IC_u1,
 
 def pinn_train(PINN, alpha, beta, gamma, xt_resid, IC_xt, IC_u1, IC_u2, BC_xt,
                BC_u, f_hat, epochs_pinn, lr_pinn):
-    loss = pinn.train_adam(PINN, lambda: PINN.loss(xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u),
-                           epochs_pinn, lr_pinn)
-    print(f"PINN Final Loss: {loss}")
+    r = pinn.train_fused(PINN, "kg", (alpha, beta, gamma), xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u,
+                         epochs_pinn, lr_pinn, xcos=PINN.xcos_x2cos2)
+    print(f"PINN Final Loss: {r['loss'].item()}")

@@ -59,9 +59,22 @@ class Mlp(C.Structure):
                 ("act", C.c_int)]
 
 
+class PinnProblem(C.Structure):
+    _fields_ = [("pde", C.c_int), ("p0", C.c_double), ("p1", C.c_double), ("p2", C.c_double),
+                ("NR", C.c_int), ("NI", C.c_int), ("NB", C.c_int),
+                ("xt_resid", C.c_void_p), ("f_hat", C.c_void_p), ("xcos", C.c_void_p), ("IC_xt", C.c_void_p),
+                ("IC_u1", C.c_void_p), ("IC_u2", C.c_void_p), ("BC_xt", C.c_void_p), ("BC_u", C.c_void_p)]
+
+
+class TrainArgs(C.Structure):
+    _fields_ = [("epochs", C.c_int), ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
+                ("eps", C.c_double), ("tol", C.c_double), ("trace_every", C.c_int),
+                ("loss_trace_dev", C.c_void_p), ("grad_out_dev", C.c_void_p)]
+
+
 EXPORTS = ("gptpinn_version", "gptpinn_last_error", "gptpinn_create", "gptpinn_destroy",
            "gptpinn_kg_sweep", "gptpinn_b_sweep", "gptpinn_ac_sweep", "gptpinn_argmax_scan",
-           "gptpinn_mlp_channels", "gptpinn_ffma_peak", "gptpinn_kg_plan")
+           "gptpinn_mlp_channels", "gptpinn_ffma_peak", "gptpinn_kg_plan", "gptpinn_pinn_train")
 
 _lib = None
 
@@ -99,6 +112,8 @@ def lib():
     L.gptpinn_kg_plan.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.POINTER(SweepArgs), C.POINTER(SweepInfo), C.POINTER(C.c_int * 6), C.POINTER(C.c_int)]
     L.gptpinn_kg_plan.restype = C.c_int
+    L.gptpinn_pinn_train.argtypes = [C.c_void_p, C.POINTER(PinnProblem), C.POINTER(Mlp), C.POINTER(TrainArgs), C.c_void_p, C.c_void_p]
+    L.gptpinn_pinn_train.restype = C.c_int
     _lib = L
     return L
 

@@ -171,6 +171,42 @@ typedef struct {
 int  gptpinn_mlp_channels(const gptpinn_mlp *mlp, const float *xt_dev, long long N,
                           float *const out_dev[5], const long long ld[5], void *stream);
 
+/* ---- fused full-PINN training ------------------------------------------------------------------
+ * Replaces the Adam loops of pinn_train (Klein-Gordon/KG_train.py:48-59 on KG_models.NN.loss,
+ * KG_models.py:92-129; Burgers/B_train.py:76-90 on B_models.NN.loss, B_models.py:79-105): all epochs run
+ * in one persistent cooperative kernel (forward-mode derivative channels, PDE residual, hand-derived
+ * reverse pass, deterministic gradient reduction, torch.optim.Adam update with default betas/eps).  */
+#define GPTPINN_PDE_KG       0
+#define GPTPINN_PDE_BURGERS  1
+typedef struct {
+    int          pde;
+    double       p0, p1, p2;        /* KG: alpha, beta, gamma            Burgers: nu                 */
+    int          NR, NI, NB;
+    const float *xt_resid;          /* [NR, 2] device, contiguous                                     */
+    const float *f_hat;             /* [NR] or NULL (zero)                                            */
+    const float *xcos;              /* [NR]  KG forcing xcos_x2cos2; NULL for Burgers                 */
+    const float *IC_xt;             /* [NI, 2]                                                        */
+    const float *IC_u1;             /* [NI]  KG IC_u1 / Burgers IC_u                                  */
+    const float *IC_u2;             /* [NI]  KG IC_u2 or NULL (zero); ignored for Burgers             */
+    const float *BC_xt;             /* [NB, 2]                                                        */
+    const float *BC_u;              /* [NB]                                                           */
+} gptpinn_pinn_problem;
+
+typedef struct {
+    int    epochs;
+    double lr, beta1, beta2, eps;   /* torch.optim.Adam defaults: 0.9, 0.999, 1e-8                    */
+    double tol;                     /* < 0: none; else stop BEFORE the step once loss < tol (B_train.py:84) */
+    int    trace_every;             /* > 0: loss_trace_dev[k] = loss before the step of epoch 1 + k*trace_every */
+    float *loss_trace_dev;          /* [(epochs-1)/trace_every + 1] or NULL                           */
+    float *grad_out_dev;            /* [n_params] or NULL: gradient of the last executed step, packed
+                                       per layer as weight (row-major [out][in]) then bias             */
+} gptpinn_train_args;
+
+/* `net->W[l]` / `net->b[l]` are updated IN PLACE (contiguous fp32 device tensors).  status_dev[0] = the last
+ * evaluated loss (what the reference prints as "PINN Final Loss"), status_dev[1] = epochs entered (float). */
+int  gptpinn_pinn_train(gptpinn_handle *h, const gptpinn_pinn_problem *prob, const gptpinn_mlp *net,
+                        const gptpinn_train_args *args, float *status_dev, void *stream);
+
 /* Host-only (no CUDA call): the work-item plan gptpinn_kg_sweep would build for this grid on a device
  * with n_sm SMs.  sl_hist[l] = number of items with 2^l sibling lanes; *covered = parameters assigned
  * (must equal Np).  Used by tests and for tuning; no reference counterpart.                            */

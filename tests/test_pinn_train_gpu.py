@@ -1,0 +1,140 @@
+"""GPU: the fused full-PINN training kernel vs torch autograd + torch.optim.Adam on the same network
+(the reference's NN.loss: KG_models.py:92-129, B_models.py:79-105).  Per-step parity: loss, every
+gradient, one Adam update; then a short trajectory.  Tolerances are fp32 (written at each assert)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _pack_grads(model):
+    return torch.cat([torch.cat([l.weight.grad.reshape(-1), l.bias.grad.reshape(-1)]) for l in model.linears])
+
+
+def _pack_params(model):
+    return torch.cat([torch.cat([l.weight.data.reshape(-1), l.bias.data.reshape(-1)]) for l in model.linears])
+
+
+def _kg_setup(nc=17, ic=45, bc=33, seed=3):
+    import KG_data
+    import KG_models
+    import KG_precomp
+    xt, f_hat, _ = KG_data.residual_data(-1.0, 1.0, 0.0, 5.0, nc, 4)
+    IC_xt, IC_u1, IC_u2, BC_xt, BC_u = KG_data.ICBC_data(-1.0, 1.0, 0.0, 5.0, bc, ic)
+    g = torch.Generator().manual_seed(seed)
+    f_hat = 0.1 * torch.randn(f_hat.shape, generator=g)              # exercise the targets too
+    IC_u2 = 0.1 * torch.randn(IC_u2.shape, generator=g)
+    t = [x.cuda() for x in (xt, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u)]
+    xcos = KG_precomp.xcos_term(t[0][:, 0:1], t[0][:, 1:2])
+    params = (-1.3, 0.4, 0.7)
+
+    def make():
+        net = KG_models.NN(np.array([2, 40, 40, 1]), *params, xcos).cuda()
+        gg = torch.Generator().manual_seed(seed + 1)
+        for lin in net.linears:                                       # non-zero biases so their gradients are tested
+            lin.bias.data = (0.1 * torch.randn(lin.bias.shape, generator=gg)).cuda()
+        return net
+    return make, params, t, xcos
+
+
+def _torch_loss_kg(net, t):
+    xt, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u = t
+    return net.loss(xt.clone().requires_grad_(), f_hat, IC_xt.clone().requires_grad_(), IC_u1, IC_u2, BC_xt, BC_u)
+
+
+def test_kg_one_step_matches_autograd_and_adam():
+    from gptpinn import pinn
+    make, params, t, xcos = _kg_setup()
+    xt, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u = t
+    ref = make()
+    opt = torch.optim.Adam(ref.parameters(), lr=5e-4)
+    loss = _torch_loss_kg(ref, t)
+    opt.zero_grad()
+    loss.backward()
+    g_ref = _pack_grads(ref).clone()
+    p0 = _pack_params(ref).clone()
+    opt.step()
+    p_ref = _pack_params(ref)
+
+    net = make()
+    r = pinn.train_fused(net, "kg", params, xt, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u, 1, 5e-4, xcos=xcos, want_grad=True)
+    torch.cuda.synchronize()
+    assert abs(float(r["loss"]) - float(loss)) <= 1e-5 * abs(float(loss))                      # loss: 1e-5 relative
+    gerr = float((r["grad"] - g_ref).abs().max() / g_ref.abs().max())
+    assert gerr < 2e-4, gerr                                                                   # gradients: 2e-4 of max |g|
+    assert pinn.epochs_done(r) == 1
+    dp_ref, dp = p_ref - p0, _pack_params(net) - p0
+    big = g_ref.abs() > 1e-3 * g_ref.abs().max()                # Adam's first step is lr*sign(g): compare where g is resolved
+    assert float((dp - dp_ref)[big].abs().max()) <= 2e-3 * 5e-4
+    assert float(dp.abs().max()) <= 1.001 * 5e-4
+
+
+def test_kg_short_trajectory_and_trace():
+    from gptpinn import pinn
+    make, params, t, xcos = _kg_setup(nc=13, ic=32, bc=20, seed=11)
+    xt, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u = t
+    ref = make()
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    ref_losses = []
+    for _ in range(25):
+        loss = _torch_loss_kg(ref, t)
+        ref_losses.append(float(loss))
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    net = make()
+    r = pinn.train_fused(net, "kg", params, xt, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u, 25, 1e-3, xcos=xcos, trace_every=1)
+    tr = r["trace"].cpu().numpy()
+    assert tr.shape == (25,)
+    assert np.max(np.abs(tr - np.array(ref_losses)) / np.array(ref_losses)) < 2e-3        # 25 chaotic-free steps: 2e-3 relative
+    assert abs(float(r["loss"]) - ref_losses[-1]) <= 2e-3 * ref_losses[-1]
+    assert tr[-1] < tr[0]
+    perr = float((_pack_params(net) - _pack_params(ref)).abs().max())
+    assert perr < 5e-4
+
+
+def test_burgers_step_tolerance_and_ragged_sizes():
+    import B_data
+    import B_models
+    from gptpinn import pinn
+    xt, f_hat, _ = B_data.residual_data(-1.0, 1.0, 0.0, 1.0, 19, 4)       # 361 points: not a multiple of 32
+    IC_xt, IC_u, BC_xt, BC_u = B_data.ICBC_data(-1.0, 1.0, 0.0, 1.0, 21, 37)
+    t = [x.cuda() for x in (xt, f_hat, IC_xt, IC_u, BC_xt, BC_u)]
+    xt, f_hat, IC_xt, IC_u, BC_xt, BC_u = t
+    nu = 0.37
+
+    def make():
+        return B_models.NN(np.array([2, 20, 20, 20, 20, 1]), nu).cuda()
+    ref = make()
+    opt = torch.optim.Adam(ref.parameters(), lr=5e-3)
+    loss = ref.loss(xt.clone().requires_grad_(), IC_xt, IC_u, BC_xt, BC_u, f_hat)
+    opt.zero_grad()
+    loss.backward()
+    g_ref = _pack_grads(ref).clone()
+    net = make()
+    p0 = _pack_params(net).clone()
+    r = pinn.train_fused(net, "burgers", (nu,), xt, f_hat, IC_xt, IC_u, None, BC_xt, BC_u, 1, 5e-3, want_grad=True)
+    assert abs(float(r["loss"]) - float(loss)) <= 1e-5 * abs(float(loss))
+    assert float((r["grad"] - g_ref).abs().max() / g_ref.abs().max()) < 2e-4
+    assert not torch.equal(_pack_params(net), p0)
+    # tolerance above the initial loss: the reference breaks BEFORE the first step (B_train.py:84)
+    net2 = make()
+    r2 = pinn.train_fused(net2, "burgers", (nu,), xt, f_hat, IC_xt, IC_u, None, BC_xt, BC_u, 50, 5e-3, tol=float(loss) * 2)
+    assert pinn.epochs_done(r2) == 1 and torch.equal(_pack_params(net2), p0)
+    assert abs(float(r2["loss"]) - float(loss)) <= 1e-5 * abs(float(loss))
+    # and a run that converges below a reachable tolerance stops early
+    net3 = make()
+    r3 = pinn.train_fused(net3, "burgers", (nu,), xt, f_hat, IC_xt, IC_u, None, BC_xt, BC_u, 400, 5e-3, tol=float(loss) * 0.5)
+    assert pinn.epochs_done(r3) < 400 and float(r3["loss"]) < float(loss) * 0.5
+
+
+def test_dropin_pinn_train_prints_and_updates(capsys):
+    import KG_train
+    make, params, t, xcos = _kg_setup(nc=9, ic=16, bc=16, seed=5)
+    xt, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u = t
+    net = make()
+    p0 = _pack_params(net).clone()
+    KG_train.pinn_train(net, *params, xt.requires_grad_(), IC_xt.requires_grad_(), IC_u1, IC_u2, BC_xt, BC_u, f_hat, 30, 5e-4)
+    assert "PINN Final Loss:" in capsys.readouterr().out
+    assert not torch.equal(_pack_params(net), p0)
