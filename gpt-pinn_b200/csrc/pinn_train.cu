@@ -289,18 +289,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pinn_train_kernel(const PinnDes
         }
         grid.sync();
         const bool stop = d.stop[0] != 0;
-        if (!stop && gtid < P) {
-            float gsum = 0.f;
-            for (int w = 0; w < d.n_partials; ++w) gsum += d.partials[(size_t)w * d.partial_stride + gtid];
-            if (d.grad_out) d.grad_out[gtid] = gsum;
-            // torch.optim.Adam (single-tensor semantics)
+        if (!stop) {
             const double bc1 = 1.0 - pow((double)d.beta1, (double)epoch);
             const double bc2 = 1.0 - pow((double)d.beta2, (double)epoch);
-            const float m = d.adam_m[gtid] = d.adam_m[gtid] + (gsum - d.adam_m[gtid]) * d.omb1;     // exp_avg.lerp_(grad, 1 - beta1)
-            const float v = d.adam_v[gtid] = fmaf(d.omb2 * gsum, gsum, d.beta2 * d.adam_v[gtid]);   // mul_(beta2).addcmul_(g, g, 1 - beta2)
             const float step_size = (float)((double)d.lr / bc1);
-            const float denom = sqrtf(v) / (float)sqrt(bc2) + d.eps;
-            d.params[gtid] = d.params[gtid] - step_size * (m / denom);
+            const float bc2_sqrt = (float)sqrt(bc2);
+            for (int i = gtid; i < P; i += gridDim.x * blockDim.x) {
+                float gsum = 0.f;
+                for (int w = 0; w < d.n_partials; ++w) gsum += d.partials[(size_t)w * d.partial_stride + i];
+                if (d.grad_out) d.grad_out[i] = gsum;
+                // torch.optim.Adam (single-tensor semantics)
+                const float m = d.adam_m[i] = d.adam_m[i] + (gsum - d.adam_m[i]) * d.omb1;     // exp_avg.lerp_(grad, 1 - beta1)
+                const float v = d.adam_v[i] = fmaf(d.omb2 * gsum, gsum, d.beta2 * d.adam_v[i]);   // mul_(beta2).addcmul_(g, g, 1 - beta2)
+                const float denom = sqrtf(v) / bc2_sqrt + d.eps;
+                d.params[i] = d.params[i] - step_size * (m / denom);
+            }
         }
         grid.sync();
         if (stop) break;
