@@ -91,6 +91,44 @@ def build_problem(device, nc=NC):
     return d, float(np.median(t_pre))
 
 
+def aux_measurements(device, d):
+    """Secondary rows of the metric: precompute seconds at N_R = 10^6 (BASELINE config 5) and the fused
+    full-PINN training step (us / Adam epoch at the KG default sizes)."""
+    import KG_models
+    from gptpinn import pinn, precomp
+    out = {}
+    nc = 1000
+    x = torch.linspace(-1.0, 1.0, nc, device=device)
+    t = torch.linspace(0.0, 5.0, nc, device=device)
+    xt = torch.stack((x.repeat(nc), t.repeat_interleave(nc)), dim=1).contiguous()
+    layers = [(w.to(device), b.to(device)) for w, b in synthetic_weights(1000)]
+    bufs = [torch.empty((nc * nc, N_NEURONS), device=device) for _ in range(3)]
+    for rep in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        precomp.mlp_channels(layers, "cos", xt, v=bufs[0][:, 3], q=bufs[1][:, 3], r=bufs[2][:, 3])
+        precomp.mlp_channels(layers, "cos", d["IC_xt"], v=d["out_IC"][:, 0], t=d["out_IC_t"][:, 0])
+        precomp.mlp_channels(layers, "cos", d["BC_xt"], v=d["out_BC"][:, 0])
+        precomp.mlp_channels(layers, "cos", d["xt_test"], v=d["out_test"][:, 0])
+        e1.record()
+        torch.cuda.synchronize()
+        out["precompute_1e6_s"] = e0.elapsed_time(e1) * 1e-3
+    del bufs, xt
+    net = KG_models.NN(np.array([2, 40, 40, 1]), -1.5, 0.5, 0.5, d["xcos"]).to(device)
+    args = (net, "kg", (-1.5, 0.5, 0.5), d["xt_resid"], d["f_hat"], d["IC_xt"], d["IC_u1"], d["IC_u2"], d["BC_xt"], d["BC_u"])
+    pinn.train_fused(*args, 10, 5e-4, xcos=d["xcos"])
+    torch.cuda.synchronize()
+    n_ep = 1000
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = pinn.train_fused(*args, n_ep, 5e-4, xcos=d["xcos"])
+    e1.record()
+    torch.cuda.synchronize()
+    out["pinn_train_us_per_epoch"] = 1e3 * e0.elapsed_time(e1) / n_ep
+    out["pinn_train_loss_after_1010_epochs"] = float(r["loss"])
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -342,6 +380,7 @@ def main():
         except Exception as e:   # the C oracle is optional test infrastructure
             cpu["c_oracle_openmp"] = {"error": str(e)}
 
+    aux = aux_measurements(device, d) if not args.no_cpu_baseline else {}
     out = {
         "metric": "param_epochs_per_sec", "value": value, "unit": "param*epochs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -354,7 +393,7 @@ def main():
                 "api": "KG_train.offline_generation (drop-in) with pinned host activation matrices"},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks, "precompute_s": {"value": precompute_s, "what": f"one neuron, all KG point sets (N_R={N}), CUDA closed-form kernel"},
-        "wall_s_timed_region": t_wall, "ffma_peak_tflops_measured": ffma_peak,
+        "wall_s_timed_region": t_wall, "ffma_peak_tflops_measured": ffma_peak, "aux": aux,
     }
     print(json.dumps(out))
     if world > 1:

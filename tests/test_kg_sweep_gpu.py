@@ -139,3 +139,39 @@ def test_argmax_scan_matches_oracle_on_random_and_ties():
         L, idx = sweep.argmax_scan(torch.from_numpy(f).cuda(), torch.from_numpy(m).cuda())
         Lo, io = oracle.argmax_scan(f, m)
         assert idx == io and float(L) == Lo, Np
+
+
+def test_kg_dense_rows_config5_properties():
+    """N_R = 10^6 rows (BASELINE config 5 size), few parameters and epochs: CUDA vs the f64 oracle, and the
+    row-permutation invariance of the update (a size-independent property of the sums over rows)."""
+    from oracle import oracle
+    rng = np.random.default_rng(1)
+    NR, NI, NB, n = 1_000_000, 512, 1024, 15
+    base = (rng.standard_normal((4096, 15)) * 0.3).astype(np.float32)
+    h = dict(out=np.tile(base, (NR // 4096 + 1, 1))[:NR] * (1 + 0.01 * rng.standard_normal((NR, 1)).astype(np.float32)))
+    h["out_xx"] = np.roll(h["out"], 1, axis=1) * 0.7
+    h["out_tt"] = np.roll(h["out"], 2, axis=1) * 0.5
+    h["out_IC"] = (rng.standard_normal((NI, 15)) * 0.3).astype(np.float32)
+    h["out_IC_t"] = (rng.standard_normal((NI, 15)) * 0.3).astype(np.float32)
+    h["out_BC"] = (rng.standard_normal((NB, 15)) * 0.3).astype(np.float32)
+    h["xcos"] = (rng.standard_normal((NR, 1)) * 0.3).astype(np.float32)
+    h["f_hat"] = np.zeros((NR, 1), np.float32)
+    h["IC_u1"] = rng.standard_normal((NI, 1)).astype(np.float32)
+    h["IC_u2"] = np.zeros((NI, 1), np.float32)
+    h["BC_u"] = rng.standard_normal((NB, 1)).astype(np.float32)
+    h = {k: np.ascontiguousarray(v.astype(np.float32)) for k, v in h.items()}
+    d = {k: torch.from_numpy(v).cuda() for k, v in h.items()}
+    grid = np.array([[-1.5, 0.5, 0.2], [-1.5, 0.5, 0.9], [-1.1, 0.1, 0.5], [-1.9, 0.8, 0.0]])
+    r = _run(d, n, grid, 6, 0.01, rec_every=2)
+    pr = oracle.kg_problem(n, *(h[k] for k in KG_NAMES))
+    o = oracle.sweep("kg", pr, grid, np.full(n, 1.0 / n, np.float32), 6, 0.01, 2, "f64")
+    assert rel_scalar(r["f"].cpu().numpy(), o["f"]) < TOL
+    assert rel_vec(r["c"].cpu().numpy(), o["c"]) < TOL
+    assert rel_scalar(r["trace"].cpu().numpy(), o["trace"]) < TOL
+    perm = torch.from_numpy(rng.permutation(NR)).cuda()
+    d2 = dict(d)
+    for k in ("out", "out_xx", "out_tt", "xcos", "f_hat"):
+        d2[k] = d[k][perm].contiguous()
+    r2 = _run(d2, n, grid, 6, 0.01)
+    assert rel_scalar(r2["f"].cpu().numpy(), r["f"].cpu().numpy()) < TOL
+    assert rel_vec(r2["c"].cpu().numpy(), r["c"].cpu().numpy()) < TOL

@@ -74,3 +74,28 @@ def test_edge_sizes():
     for N in (1, 31, 129):
         ch = _eval(L, "cos", g["xt_resid"][:N], "vq")
         assert _col_err(ch["v"], g["out"][:N, 0]) < PRE_TOL
+
+
+def test_dense_million_points_config5():
+    """BASELINE config 5 size (N_R = 10^6): spot-check 4096 random points against the oracle, check that the
+    result does not depend on the batch it was computed in (per-point determinism)."""
+    from oracle import oracle
+    from gptpinn import precomp
+    g = load_golden("kg_small")
+    L = _layers(g, 3)
+    nc = 1000
+    x = torch.linspace(-1.0, 1.0, nc, device="cuda")
+    t = torch.linspace(0.0, 5.0, nc, device="cuda")
+    xt = torch.stack((x.repeat(nc), t.repeat_interleave(nc)), dim=1).contiguous()
+    bufs = {k: torch.empty((nc * nc, 15), device="cuda") for k in "vqr"}
+    precomp.mlp_channels(L, "cos", xt, **{k: bufs[k][:, 7] for k in "vqr"})
+    torch.cuda.synchronize()
+    idx = torch.from_numpy(np.random.default_rng(0).choice(nc * nc, 4096, replace=False)).cuda()
+    o = oracle.mlp_channels([2, 40, 40, 1], [w.cpu().numpy() for w, _ in L], [b.cpu().numpy() for _, b in L], "cos",
+                            xt[idx].cpu().numpy())
+    for k in "vqr":
+        assert _col_err(bufs[k][idx, 7].cpu().numpy(), o[k]) < PRE_TOL
+    sub = {k: torch.empty(4096, device="cuda") for k in "vqr"}
+    precomp.mlp_channels(L, "cos", xt[idx].contiguous(), **sub)
+    for k in "vqr":
+        assert torch.equal(sub[k], bufs[k][idx, 7])
