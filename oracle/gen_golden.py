@@ -393,8 +393,37 @@ def gen_ac_small():
     print("wrote ac_small")
 
 
+def gen_kg_greedy():
+    """The greedy outer loop of KG_main.py:100-138 with the full-PINN training replaced by fixed synthetic
+    weights (training is chaotic and not reproducible across implementations; everything else -- inputs(),
+    the grid bookkeeping, offline_generation and the neuron hand-over -- is the reference's own code)."""
+    nmax = 6
+    m, p = kg_problem(24, 64, 64, 10, nmax)           # same point sets / weights as kg_small's first six neurons
+    N, NI, NB = p["out"].shape[0], p["out_IC"].shape[0], p["out_BC"].shape[0]
+    kg_train = kg_grid(4, 3, 5)
+    neurons = np.zeros((nmax, 3))
+    neurons[0] = (np.median(np.linspace(-2, -1, 4)), np.median(np.linspace(0, 1, 3)), np.median(np.linspace(0, 1, 5)))
+    loss_list = np.zeros(nmax)
+    sizes = []
+    for i, neuron in enumerate(neurons):
+        kg_train = np.delete(kg_train, np.where(np.all(kg_train == neuron, axis=1))[0], axis=0)      # KG_main.py:102
+        sizes.append(len(kg_train))
+        n = i + 1
+        v = {k: p[k][:, :n] for k in ("out", "out_xx", "out_tt", "out_IC", "out_IC_t", "out_BC")}
+        L, case = m["KG_train"].offline_generation(
+            kg_train, torch.full((n,), 1.0 / n), N, NI, NB, p["IC_u1"], p["IC_u2"], p["BC_u"], p["xcos"],
+            v["out"], v["out_xx"], v["out_tt"], v["out_IC"], v["out_IC_t"], v["out_BC"], p["f_hat"], 200, 0.025)
+        loss_list[i] = L
+        if i + 1 < nmax:
+            neurons[i + 1] = case
+        print("kg_greedy stage", i, "L", float(L), "case", case, flush=True)
+    np.savez_compressed(os.path.join(OUT, "kg_greedy.npz"), neurons=neurons, loss_list=loss_list, sizes=np.array(sizes),
+                        epochs=200, lr=0.025, nmax=nmax)
+    print("wrote kg_greedy")
+
+
 GENS = {"kg_small": gen_kg_small, "kg_nonmono": gen_kg_nonmono, "kg_full": gen_kg_full,
-        "b_small": gen_b_small, "ac_small": gen_ac_small}
+        "b_small": gen_b_small, "ac_small": gen_ac_small, "kg_greedy": gen_kg_greedy}
 
 if __name__ == "__main__":
     torch.set_num_threads(int(os.environ.get("OMP_NUM_THREADS", "8")))

@@ -178,3 +178,45 @@ def test_allen_cahn_dropin():
     losses = AC_test.gpt_test_loss(g["test_mu"], *args)
     assert losses.shape == g["test_losses"].shape == (int(g["test_epochs"]) + 1, len(g["test_mu"]))
     assert rel_scalar(losses, g["test_losses"]) < TOL
+
+
+def test_kg_greedy_outer_loop_selects_the_reference_neuron_sequence():
+    """KG_main.py:100-138 with fixed synthetic PINN weights per stage (golden from the reference's own
+    inputs() + offline_generation): the drop-in inputs() + offline_generation must hand over the identical
+    neuron sequence, stage by stage, with the grid shrinking exactly as the reference's does."""
+    import KG_models
+    import KG_precomp
+    import KG_train
+    g = load_golden("kg_greedy")
+    s = load_golden("kg_small")
+    nmax = int(g["nmax"])
+    xt, IC_xt, BC_xt, xt_test = (_cuda(s[k]) for k in ("xt_resid", "IC_xt", "BC_xt", "xt_test"))
+    d = {k: _cuda(s[k]) for k in ("xcos", "f_hat", "IC_u1", "IC_u2", "BC_u")}
+    N, NI, NB, NT = xt.shape[0], IC_xt.shape[0], BC_xt.shape[0], xt_test.shape[0]
+    buf = {k: torch.ones((r, nmax), device="cuda") for k, r in
+           (("out", N), ("out_xx", N), ("out_tt", N), ("out_IC", NI), ("out_IC_t", NI), ("out_BC", NB))}
+    out_test = torch.zeros((NT, nmax), device="cuda")
+    alpha, beta, gamma = np.linspace(-2, -1, 4), np.linspace(0, 1, 3), np.linspace(0, 1, 5)
+    kg_train = np.array(np.meshgrid(alpha, beta, gamma)).T.reshape(-1, 3)
+    neurons = np.zeros((nmax, 3))
+    neurons[0] = (np.median(alpha), np.median(beta), np.median(gamma))
+    loss_list = np.zeros(nmax)
+    for i, neuron in enumerate(neurons):
+        kg_train = np.delete(kg_train, np.where(np.all(kg_train == neuron, axis=1))[0], axis=0)
+        assert len(kg_train) == int(g["sizes"][i])
+        pinn = KG_models.NN(np.array([2, 40, 40, 1]), *neuron, d["xcos"]).to("cuda")
+        for l, lin in enumerate(pinn.linears):                         # stage i's "trained" network = fixed weights
+            lin.weight.data = _cuda(s[f"pinn{i}_W{l}"])
+            lin.bias.data = _cuda(s[f"pinn{i}_b{l}"])
+        v = KG_precomp.inputs(pinn, xt, buf["out"], buf["out_xx"], buf["out_tt"], buf["out_IC_t"], buf["out_IC"],
+                              buf["out_BC"], IC_xt, BC_xt, i, out_test, xt_test)
+        train_out, train_out_xx, train_out_tt, train_out_IC_t, train_out_IC, train_out_BC = v
+        c_initial = torch.full((1, i + 1), 1 / (i + 1)).to("cuda")[0]
+        L, case = KG_train.offline_generation(kg_train, c_initial, N, NI, NB, d["IC_u1"], d["IC_u2"], d["BC_u"], d["xcos"],
+                                              train_out, train_out_xx, train_out_tt, train_out_IC, train_out_IC_t,
+                                              train_out_BC, d["f_hat"], int(g["epochs"]), float(g["lr"]))
+        loss_list[i] = L
+        if i + 1 < nmax:
+            neurons[i + 1] = case
+    assert np.array_equal(neurons, g["neurons"])
+    assert np.max(np.abs(loss_list - g["loss_list"]) / g["loss_list"]) < 2e-5
