@@ -3,18 +3,22 @@
 //
 // Replaces the reference's pinn_train loops (Klein-Gordon/KG_train.py:48-59 with KG_models.py:84-129,
 // Burgers/B_train.py:76-90 with B_models.py:70-105): per epoch the reference builds a triple-nested
-// autograd graph (grad of grad of grad) with ~100 kernel launches and an optimizer step; here
-//   phase 1  every warp takes 32 collocation / IC / BC points, one point per lane:
-//            forward-mode propagation of (u, u_x, u_t, q, r) through the MLP (q = u_xx+u_xt,
-//            r = u_tt+u_xt: the reference's mixed second derivatives), the PDE
-//            residual and its adjoints, then the hand-derived reverse pass through the same
-//            five channels (needs sigma', sigma'', sigma'''); weight gradients are formed per
-//            warp as small outer-product GEMMs staged through shared memory and accumulated in a
-//            per-warp shared buffer (each weight owned by exactly one lane: no atomics);
+// autograd graph (grad of grad of grad) with ~100 kernel launches and an optimizer step.  Here one
+// epoch is
+//   phase 1  a block of 4 warps takes a tile of 32 collocation / IC / BC points.  Thread = (point,
+//            neuron group): lane = point, warp = one quarter of every hidden layer's neurons.  The five
+//            derivative channels (u, u_x, u_t, q = u_xx+u_xt, r = u_tt+u_xt: the reference's mixed second
+//            derivatives) of the thread's own neurons stay in registers for the whole
+//            forward + reverse sweep; only the operands every thread of a point needs (the previous
+//            layer's activations, or the next layer's adjoints) are staged through shared memory, so each
+//            layer is a small GEMM  [neurons] x [neurons] x [5 channels x 32 points]  with weights read
+//            as warp-wide broadcasts.  The reverse pass is hand-derived (uses sigma', sigma'', sigma''');
+//            weight gradients are outer-product GEMMs over (channel, point) with a register tile per
+//            lane, K split over the four warps, combined in shared memory (no atomics, fixed order);
 //   grid.sync
-//   phase 2  a deterministic reduction of the per-warp partial gradients and losses, the
-//            tolerance test of B_train.py:84 (checked BEFORE the step) and torch.optim.Adam's
-//            update (beta = (0.9, 0.999), eps = 1e-8, bias correction in double);
+//   phase 2  deterministic reduction of the per-block partial gradients and losses, the tolerance test
+//            of B_train.py:84 (checked BEFORE the step) and torch.optim.Adam's update (bias correction
+//            in double);
 //   grid.sync
 // so the weights never leave the device and the host launches once per training run.
 #include <cooperative_groups.h>
@@ -29,13 +33,9 @@ namespace cg = cooperative_groups;
 namespace gp {
 
 constexpr int CH = 5;                 // v, x, t, q, r
-constexpr int WARPS = 8;              // warps per block
-constexpr int JG = 4, IG = 8;         // lane tiling of a weight matrix: 4 output groups x 8 input groups
-
-template <int WMAX>
-struct Lane {
-    float z[PINN_MAX_HIDDEN][CH][WMAX];      // pre-activations of every hidden layer (this lane's point)
-};
+constexpr int NG = 4;                 // neuron groups = warps per block
+constexpr int PT = 32;                // points per tile = lanes
+constexpr int TJG = 4, TIG = 8;       // lane tiling of a weight-gradient matrix: 4 output groups x 8 input groups
 
 __device__ __forceinline__ void act_derivs(int act, float z, float &s0, float &s1, float &s2, float &s3)
 {
@@ -49,105 +49,183 @@ __device__ __forceinline__ void act_derivs(int act, float z, float &s0, float &s
     }
 }
 
-// activations of hidden layer `l` (l >= 1) or the network inputs (l == 0) for channel set of this lane
-template <int WMAX>
-__device__ __forceinline__ void activations(const PinnDesc &d, const Lane<WMAX> &L, int l, float x, float t, int j, float (&a)[CH])
+// five channels of a = sigma(z) from the five channels of z
+__device__ __forceinline__ void act_forward(int act, const float (&z)[CH], float (&a)[CH])
 {
-    if (l == 0) {
-        a[0] = j == 0 ? x : t; a[1] = j == 0 ? 1.f : 0.f; a[2] = j == 0 ? 0.f : 1.f; a[3] = 0.f; a[4] = 0.f;
-        return;
-    }
-    const float zv = L.z[l - 1][0][j], zx = L.z[l - 1][1][j], zt = L.z[l - 1][2][j];
     float s0, s1, s2, s3;
-    act_derivs(d.act, zv, s0, s1, s2, s3);
+    act_derivs(act, z[0], s0, s1, s2, s3);
     a[0] = s0;
-    a[1] = s1 * zx;
-    a[2] = s1 * zt;
-    a[3] = fmaf(s2 * zx, zx + zt, s1 * L.z[l - 1][3][j]);
-    a[4] = fmaf(s2 * zt, zt + zx, s1 * L.z[l - 1][4][j]);
+    a[1] = s1 * z[1];
+    a[2] = s1 * z[2];
+    a[3] = fmaf(s2 * z[1], z[1] + z[2], s1 * z[3]);
+    a[4] = fmaf(s2 * z[2], z[2] + z[1], s1 * z[4]);
 }
 
-template <int WMAX>
-__global__ void __launch_bounds__(WARPS * 32, 1) pinn_train_kernel(const PinnDesc d)
+// adjoint of the five channels of z given the adjoint of the five channels of a = sigma(z)
+__device__ __forceinline__ void act_backward(int act, const float (&z)[CH], const float (&ab)[CH], float (&zb)[CH])
 {
-    cg::grid_group grid = cg::this_grid();
-    extern __shared__ float smem[];
-    const int nl = d.nlayers;                       // entries of layers[]; nl-1 linear maps, nl-2 hidden layers
-    const int P = d.n_params;
-    float *w_s = smem;                              // [P] weights + biases, packed layer after layer (W then b)
-    float *warp_base = smem + ((P + 3) & ~3);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int per_warp = ((P + 3) & ~3) + 2 * 32 * WMAX + 8;
-    float *g_s = warp_base + (size_t)warp * per_warp;            // [P] this warp's gradient partial
-    float *zb_s = g_s + ((P + 3) & ~3);                          // [32][WMAX] staged z-bar of one channel
-    float *ap_s = zb_s + 32 * WMAX;                              // [32][WMAX] staged previous activations of one channel
-    const int gwarp = blockIdx.x * WARPS + warp;
-    const int nwarps = gridDim.x * WARPS;
-    const int jg = lane / IG, ig = lane % IG;
+    float s0, s1, s2, s3;
+    act_derivs(act, z[0], s0, s1, s2, s3);
+    const float zx = z[1], zt = z[2];
+    zb[3] = s1 * ab[3];
+    zb[4] = s1 * ab[4];
+    zb[1] = fmaf(s1, ab[1], s2 * fmaf(ab[3], 2.f * zx + zt, ab[4] * zt));
+    zb[2] = fmaf(s1, ab[2], s2 * fmaf(ab[3], zx, ab[4] * (2.f * zt + zx)));
+    zb[0] = s1 * ab[0] + s2 * (zx * ab[1] + zt * ab[2] + z[3] * ab[3] + z[4] * ab[4])
+          + s3 * (ab[3] * zx * (zx + zt) + ab[4] * zt * (zt + zx));
+}
 
-    int woff[PINN_MAX_HIDDEN + 1], boff[PINN_MAX_HIDDEN + 1];
+// WMAX: widest hidden layer (all hidden layers are padded to it), NH: hidden layers (KG 2, Burgers 4)
+template <int WMAX, int NH>
+__global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d)
+{
+    constexpr int GJ = WMAX / NG;                            // neurons per warp (10 / 5)
+    constexpr int GJP = (GJ + 3) & ~3;                       // padded to a float4 multiple (12 / 8)
+    constexpr int TJ = (WMAX + TJG - 1) / TJG, TI = (WMAX + TIG - 1) / TIG;
+    constexpr int NS = CH * PT + 1;                          // neuron stride of a staging buffer (odd: conflict-free column reads)
+    constexpr int STG = WMAX * NS;                           // one staging buffer [neuron][channel][point]
+    constexpr int NHH = NH > 1 ? NH - 1 : 1;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) float smem[];
+    const int P = d.n_params;
+    const int P4 = (P + 3) & ~3;
+    float *w_s = smem;                                       // [P]   packed parameters (W row-major [out][in], then b, per layer)
+    float *g_s = w_s + P4;                                   // [P]   this block's gradient partial
+    float *wt_s = g_s + P4;                                  // [NH-1][WMAX][NG][GJP]  hidden->hidden weights, transposed + padded:  wt[l][i][jg][jj] = W[jg*GJ+jj][i]
+    float *wp_s = wt_s + (NH - 1) * WMAX * NG * GJP;         // [NH-1][WMAX][NG][GJP]  same weights, row-major + padded:          wp[l][j][ig][ii] = W[j][ig*GJ+ii]
+    float *A_s = wp_s + (NH - 1) * WMAX * NG * GJP;          // [WMAX][CH][PT]
+    float *B_s = A_s + STG;                                  // [WMAX][CH][PT]
+    float *U_s = B_s + STG;                                  // [NG][CH][PT] partial network outputs
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j0 = warp * GJ;                                // first neuron owned by this thread in every hidden layer
+    const int tjg = lane / TIG, tig = lane % TIG;
+
+    int woff[NH + 1], boff[NH + 1];
     {
         int off = 0;
-        for (int l = 0; l < nl - 1; ++l) {
+#pragma unroll
+        for (int l = 0; l <= NH; ++l) {
             woff[l] = off; off += d.layers[l] * d.layers[l + 1];
             boff[l] = off; off += d.layers[l + 1];
         }
     }
-    const int chunksR = (d.NR + 31) / 32, chunksI = (d.NI + 31) / 32, chunksB = (d.NB + 31) / 32;
-    const int nchunks = chunksR + chunksI + chunksB;
+    const int tilesR = (d.NR + PT - 1) / PT, tilesI = (d.NI + PT - 1) / PT, tilesB = (d.NB + PT - 1) / PT;
+    const int ntiles = tilesR + tilesI + tilesB;
 
-    constexpr int TJ = (WMAX + JG - 1) / JG, TI = (WMAX + IG - 1) / IG;
-    Lane<WMAX> L;
     for (int epoch = 1; epoch <= d.epochs; ++epoch) {
         // -------------------------------------------------------------- phase 1
-        for (int i = threadIdx.x; i < P; i += blockDim.x) w_s[i] = d.params[i];
-        for (int i = lane; i < P; i += 32) g_s[i] = 0.f;
+        for (int i = threadIdx.x; i < P; i += blockDim.x) { w_s[i] = d.params[i]; g_s[i] = 0.f; }
         __syncthreads();
-        float lossR = 0.f, lossI1 = 0.f, lossI2 = 0.f, lossB = 0.f;
+        for (int l = 1; l < NH; ++l) {                       // padded copies of the hidden->hidden matrices
+            const float *W = w_s + woff[l];
+            const int wi = d.layers[l], wo = d.layers[l + 1];
+            float *wt = wt_s + (l - 1) * WMAX * NG * GJP, *wp = wp_s + (l - 1) * WMAX * NG * GJP;
+            for (int e = threadIdx.x; e < WMAX * NG * GJP; e += blockDim.x) {
+                const int a = e / (NG * GJP), g = (e / GJP) % NG, s = e % GJP;
+                const int b = g * GJ + s;
+                wt[e] = (s < GJ && b < wo && a < wi) ? W[b * wi + a] : 0.f;      // wt[i=a][g][s] = W[j=b][i=a]
+                wp[e] = (s < GJ && a < wo && b < wi) ? W[a * wi + b] : 0.f;      // wp[j=a][g][s] = W[j=a][i=b]
+            }
+        }
+        __syncthreads();
+        float lossR = 0.f, lossI1 = 0.f, lossI2 = 0.f, lossB = 0.f;          // accumulated by warp 0 only
+        float wacc[NHH][TJ][TI];                                            // weight-gradient tiles of the hidden->hidden layers
+#pragma unroll
+        for (int l = 0; l < NHH; ++l)
+#pragma unroll
+            for (int a = 0; a < TJ; ++a)
+#pragma unroll
+                for (int b = 0; b < TI; ++b) wacc[l][a][b] = 0.f;
 
-        for (int chunk = gwarp; chunk < nchunks; chunk += nwarps) {
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             int kind, p;                              // 0 residual, 1 IC, 2 BC
-            if (chunk < chunksR) { kind = 0; p = chunk * 32 + lane; }
-            else if (chunk < chunksR + chunksI) { kind = 1; p = (chunk - chunksR) * 32 + lane; }
-            else { kind = 2; p = (chunk - chunksR - chunksI) * 32 + lane; }
+            if (tile < tilesR) { kind = 0; p = tile * PT + lane; }
+            else if (tile < tilesR + tilesI) { kind = 1; p = (tile - tilesR) * PT + lane; }
+            else { kind = 2; p = (tile - tilesR - tilesI) * PT + lane; }
             const int np = kind == 0 ? d.NR : (kind == 1 ? d.NI : d.NB);
             const bool live = p < np;
             const float *xt = kind == 0 ? d.xt_resid : (kind == 1 ? d.IC_xt : d.BC_xt);
             const float x = live ? xt[2 * p] : 0.f, t = live ? xt[2 * p + 1] : 0.f;
 
-            // ---- forward: five channels through every layer
-            float u[CH];
-            float a[CH][WMAX];                               // input activations of the current linear map
-            a[0][0] = x; a[1][0] = 1.f; a[2][0] = 0.f; a[3][0] = 0.f; a[4][0] = 0.f;
-            a[0][1] = t; a[1][1] = 0.f; a[2][1] = 1.f; a[3][1] = 0.f; a[4][1] = 0.f;
-            for (int l = 0; l < nl - 1; ++l) {
-                const int wi = d.layers[l], wo = d.layers[l + 1];
-                const float *W = w_s + woff[l], *B = w_s + boff[l];
-                for (int j = 0; j < wo; ++j) {
-                    float acc[CH] = {B[j], 0.f, 0.f, 0.f, 0.f};
-                    for (int i = 0; i < wi; ++i) {
-                        const float wv = W[j * wi + i];
+            // ================================ forward ================================
+            float z[NH][CH][GJ];                      // pre-activations of this thread's neurons, every hidden layer
+            {
+                const float *W = w_s + woff[0], *Bv = w_s + boff[0];       // layer 0: inputs (x, t), channels known in closed form
 #pragma unroll
-                        for (int c = 0; c < CH; ++c) acc[c] = fmaf(wv, a[c][i], acc[c]);
-                    }
-                    if (l < nl - 2) {
-#pragma unroll
-                        for (int c = 0; c < CH; ++c) L.z[l][c][j] = acc[c];
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < CH; ++c) u[c] = acc[c];
-                    }
+                for (int jj = 0; jj < GJ; ++jj) {
+                    const int j = j0 + jj;
+                    const bool ok = j < d.layers[1];
+                    const float wx = ok ? W[j * 2] : 0.f, wt0 = ok ? W[j * 2 + 1] : 0.f;
+                    z[0][0][jj] = ok ? fmaf(wx, x, fmaf(wt0, t, Bv[j])) : 0.f;
+                    z[0][1][jj] = wx; z[0][2][jj] = wt0; z[0][3][jj] = 0.f; z[0][4][jj] = 0.f;
                 }
-                if (l < nl - 2)
-                    for (int j = 0; j < wo; ++j) {
-                        float av[CH];
-                        activations<WMAX>(d, L, l + 1, x, t, j, av);
+            }
 #pragma unroll
-                        for (int c = 0; c < CH; ++c) a[c][j] = av[c];
+            for (int l = 0; l < NH; ++l) {
+                // activations of hidden layer l for the thread's own neurons -> staging buffer A
+#pragma unroll
+                for (int jj = 0; jj < GJ; ++jj) {
+                    float zz[CH], aa[CH];
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) zz[c] = z[l][c][jj];
+                    act_forward(d.act, zz, aa);
+                    const bool ok = (j0 + jj) < d.layers[l + 1];
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) A_s[(j0 + jj) * NS + c * PT + lane] = ok ? aa[c] : 0.f;
+                }
+                __syncthreads();
+                if (l < NH - 1) {
+                    // z_{l+1}[c][j] = b[j] + sum_i W[j][i] a_l[c][i]   (weights as warp-wide broadcasts)
+                    const float *wt = wt_s + l * WMAX * NG * GJP + warp * GJP;
+                    const float *Bv = w_s + boff[l + 1];
+#pragma unroll
+                    for (int jj = 0; jj < GJ; ++jj) {
+                        z[l + 1][0][jj] = (j0 + jj) < d.layers[l + 2] ? Bv[j0 + jj] : 0.f;
+#pragma unroll
+                        for (int c = 1; c < CH; ++c) z[l + 1][c][jj] = 0.f;
                     }
+                    const int wi = d.layers[l + 1];
+                    for (int i = 0; i < wi; ++i) {
+                        float av[CH], wv[GJP];
+#pragma unroll
+                        for (int c = 0; c < CH; ++c) av[c] = A_s[i * NS + c * PT + lane];
+#pragma unroll
+                        for (int s = 0; s < GJP; s += 4) {
+                            const float4 w4 = *reinterpret_cast<const float4 *>(wt + i * NG * GJP + s);
+                            wv[s] = w4.x; wv[s + 1] = w4.y; wv[s + 2] = w4.z; wv[s + 3] = w4.w;
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < GJ; ++jj)
+#pragma unroll
+                            for (int c = 0; c < CH; ++c) z[l + 1][c][jj] = fmaf(wv[jj], av[c], z[l + 1][c][jj]);
+                    }
+                    __syncthreads();                  // A is rewritten by the next layer
+                }
+            }
+            // output layer (one linear unit): partial over the thread's neurons, then over the four warps
+            float u[CH];
+            {
+                const float *W = w_s + woff[NH];
+                float pu[CH] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int jj = 0; jj < GJ; ++jj) {
+                    const float wv = (j0 + jj) < d.layers[NH] ? W[j0 + jj] : 0.f;
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) pu[c] = fmaf(wv, A_s[(j0 + jj) * NS + c * PT + lane], pu[c]);
+                }
+#pragma unroll
+                for (int c = 0; c < CH; ++c) U_s[(warp * CH + c) * PT + lane] = pu[c];
+                __syncthreads();
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    float s = c == 0 ? w_s[boff[NH]] : 0.f;
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) s += U_s[(g * CH + c) * PT + lane];
+                    u[c] = s;
+                }
             }
 
-            // ---- loss terms and output adjoints
+            // ================================ loss terms and output adjoints ================================
             float ub[CH] = {0.f, 0.f, 0.f, 0.f, 0.f};
             if (live) {
                 if (kind == 0) {
@@ -176,133 +254,203 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pinn_train_kernel(const PinnDes
                 }
             }
 
-            // ---- reverse pass.  zbar = adjoint of the pre-activations of the layer being processed
-            float zbar[CH][WMAX];
+            // ================================ reverse ================================
+            // output layer: Wbar_out[j] += sum_{c,p} ub_c a_{NH-1}[c][j];  bbar_out += sum_p ub_v;  abar[c][j] = W_out[j] ub_c
+            float ab[CH][GJ];                         // adjoint of the activations, then of the pre-activations (in place)
+            {
+                const float *W = w_s + woff[NH];
 #pragma unroll
-            for (int c = 0; c < CH; ++c) zbar[c][0] = ub[c];           // output layer: one unit, linear
-            for (int l = nl - 2; l >= 0; --l) {
-                const int wi = d.layers[l], wo = d.layers[l + 1];
-                const float *W = w_s + woff[l];
-                // (1) weight / bias gradients of layer l:  Wbar[j][i] += sum_{c, points} zbar_c[j] * a_c^{(l)}[i]
-                //     a small GEMM per warp: lane (jg, ig) owns a TJ x TI block of the weight matrix
-                for (int i = 0; i < wi; ++i) {
-                    float av[CH];
-                    activations<WMAX>(d, L, l, x, t, i, av);
+                for (int jj = 0; jj < GJ; ++jj) {
+                    const bool ok = (j0 + jj) < d.layers[NH];
+                    float s = 0.f;
 #pragma unroll
-                    for (int c = 0; c < CH; ++c) a[c][i] = av[c];
+                    for (int c = 0; c < CH; ++c) s = fmaf(ub[c], A_s[(j0 + jj) * NS + c * PT + lane], s);
+                    for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                    if (lane == 0 && ok) g_s[woff[NH] + j0 + jj] += s;
+                    const float wv = ok ? W[j0 + jj] : 0.f;
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) ab[c][jj] = wv * ub[c];
                 }
-                float acc[TJ][TI];
+                if (warp == 0) {
+                    float s = ub[0];
+                    for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                    if (lane == 0) g_s[boff[NH]] += s;
+                }
+            }
+            __syncthreads();                          // all reads of A (activations of the last hidden layer) are done
 #pragma unroll
-                for (int tj = 0; tj < TJ; ++tj)
+            for (int l = NH - 1; l >= 0; --l) {
+                // through the activation of hidden layer l: ab <- zbar
 #pragma unroll
-                    for (int ti = 0; ti < TI; ++ti) acc[tj][ti] = 0.f;
-                for (int c = 0; c < CH; ++c) {
-                    for (int j = 0; j < wo; ++j) zb_s[lane * WMAX + j] = zbar[c][j];
-                    for (int j = wo; j < WMAX; ++j) zb_s[lane * WMAX + j] = 0.f;
-                    for (int i = 0; i < wi; ++i) ap_s[lane * WMAX + i] = a[c][i];
-                    for (int i = wi; i < WMAX; ++i) ap_s[lane * WMAX + i] = 0.f;
-                    __syncwarp();
-                    for (int q = 0; q < 32; ++q) {
-                        float zv[TJ], av[TI];
+                for (int jj = 0; jj < GJ; ++jj) {
+                    float zz[CH], aa[CH], zb[CH];
 #pragma unroll
-                        for (int tj = 0; tj < TJ; ++tj) zv[tj] = zb_s[q * WMAX + jg * TJ + tj];
+                    for (int c = 0; c < CH; ++c) { zz[c] = z[l][c][jj]; aa[c] = ab[c][jj]; }
+                    act_backward(d.act, zz, aa, zb);
 #pragma unroll
-                        for (int ti = 0; ti < TI; ++ti) { const int i = ig * TI + ti; av[ti] = i < WMAX ? ap_s[q * WMAX + i] : 0.f; }
+                    for (int c = 0; c < CH; ++c) ab[c][jj] = zb[c];
+                }
+                // bias gradient of the linear map feeding hidden layer l: bbar[j] += sum_p zbar_v[j]
 #pragma unroll
-                        for (int tj = 0; tj < TJ; ++tj)
+                for (int jj = 0; jj < GJ; ++jj) {
+                    float s = ab[0][jj];
+                    for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                    if (lane == 0 && (j0 + jj) < d.layers[l + 1]) g_s[boff[l] + j0 + jj] += s;
+                }
+                if (l == 0) {
+                    // first linear map: inputs (x, t) with channels (x,1,0,0,0) and (t,0,1,0,0)
 #pragma unroll
-                            for (int ti = 0; ti < TI; ++ti) acc[tj][ti] = fmaf(zv[tj], av[ti], acc[tj][ti]);
-                    }
-                    if (c == 0)                                       // bias: only the value channel carries b
-                        for (int j = lane; j < wo; j += 32) {
-                            float bs = 0.f;
-                            for (int q = 0; q < 32; ++q) bs += zb_s[q * WMAX + j];
-                            g_s[boff[l] + j] += bs;
+                    for (int jj = 0; jj < GJ; ++jj) {
+                        float sx = fmaf(ab[0][jj], x, ab[1][jj]), st = fmaf(ab[0][jj], t, ab[2][jj]);
+                        for (int off = 16; off; off >>= 1) {
+                            sx += __shfl_xor_sync(0xffffffffu, sx, off);
+                            st += __shfl_xor_sync(0xffffffffu, st, off);
                         }
-                    __syncwarp();
-                }
-#pragma unroll
-                for (int tj = 0; tj < TJ; ++tj) {
-                    const int j = jg * TJ + tj;
-#pragma unroll
-                    for (int ti = 0; ti < TI; ++ti) {
-                        const int i = ig * TI + ti;
-                        if (j < wo && i < wi) g_s[woff[l] + j * wi + i] += acc[tj][ti];
+                        if (lane == 0 && (j0 + jj) < d.layers[1]) {
+                            g_s[woff[0] + (j0 + jj) * 2] += sx;
+                            g_s[woff[0] + (j0 + jj) * 2 + 1] += st;
+                        }
                     }
-                }
-                if (l == 0) break;
-                // (2) adjoint of the activations of hidden layer l (index l-1 in L.z): abar_c[i] = sum_j W[j][i] zbar_c[j]
-                //     then through the activation to the pre-activations of that hidden layer
-                float nz[CH][WMAX];
-                for (int i = 0; i < wi; ++i) {
-                    float ab[CH] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                } else {
+                    // stage zbar (B) and the activations of hidden layer l-1 (A) for the two GEMMs
+#pragma unroll
+                    for (int jj = 0; jj < GJ; ++jj) {
+                        float zz[CH], aa[CH];
+#pragma unroll
+                        for (int c = 0; c < CH; ++c) zz[c] = z[l - 1][c][jj];
+                        act_forward(d.act, zz, aa);
+                        const bool okA = (j0 + jj) < d.layers[l], okB = (j0 + jj) < d.layers[l + 1];
+#pragma unroll
+                        for (int c = 0; c < CH; ++c) {
+                            A_s[(j0 + jj) * NS + c * PT + lane] = okA ? aa[c] : 0.f;
+                            B_s[(j0 + jj) * NS + c * PT + lane] = okB ? ab[c][jj] : 0.f;
+                        }
+                    }
+                    __syncthreads();
+                    // weight gradient of map l (hidden l-1 -> hidden l): Wbar[j][i] += sum_{c,p} zbar[c][j][p] a[c][i][p];
+                    // lane (tjg, tig) owns a TJ x TI tile, warp w takes points 8w .. 8w+7 of every channel
+                    for (int c = 0; c < CH; ++c) {
+#pragma unroll
+                        for (int q8 = 0; q8 < PT / NG; ++q8) {
+                            const int q = warp * (PT / NG) + q8;
+                            float zv[TJ], av[TI];
+#pragma unroll
+                            for (int a = 0; a < TJ; ++a) { const int j = tjg * TJ + a; zv[a] = j < WMAX ? B_s[j * NS + c * PT + q] : 0.f; }
+#pragma unroll
+                            for (int b = 0; b < TI; ++b) { const int i = tig * TI + b; av[b] = i < WMAX ? A_s[i * NS + c * PT + q] : 0.f; }
+#pragma unroll
+                            for (int a = 0; a < TJ; ++a)
+#pragma unroll
+                                for (int b = 0; b < TI; ++b) wacc[l > 0 ? l - 1 : 0][a][b] = fmaf(zv[a], av[b], wacc[l > 0 ? l - 1 : 0][a][b]);
+                        }
+                    }
+                    // adjoint of the activations of hidden layer l-1: abar[c][i] = sum_j W[j][i] zbar[c][j]
+                    const float *wp = wp_s + (l > 0 ? l - 1 : 0) * WMAX * NG * GJP + warp * GJP;
+#pragma unroll
+                    for (int jj = 0; jj < GJ; ++jj)
+#pragma unroll
+                        for (int c = 0; c < CH; ++c) ab[c][jj] = 0.f;
+                    const int wo = d.layers[l + 1];
                     for (int j = 0; j < wo; ++j) {
-                        const float wv = W[j * wi + i];
+                        float zv[CH], wv[GJP];
 #pragma unroll
-                        for (int c = 0; c < CH; ++c) ab[c] = fmaf(wv, zbar[c][j], ab[c]);
+                        for (int c = 0; c < CH; ++c) zv[c] = B_s[j * NS + c * PT + lane];
+#pragma unroll
+                        for (int s = 0; s < GJP; s += 4) {
+                            const float4 w4 = *reinterpret_cast<const float4 *>(wp + j * NG * GJP + s);
+                            wv[s] = w4.x; wv[s + 1] = w4.y; wv[s + 2] = w4.z; wv[s + 3] = w4.w;
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < GJ; ++jj)
+#pragma unroll
+                            for (int c = 0; c < CH; ++c) ab[c][jj] = fmaf(wv[jj], zv[c], ab[c][jj]);
                     }
-                    const float zv = L.z[l - 1][0][i], zx = L.z[l - 1][1][i], zt = L.z[l - 1][2][i];
-                    const float zq = L.z[l - 1][3][i], zr = L.z[l - 1][4][i];
-                    float s0, s1, s2, s3;
-                    act_derivs(d.act, zv, s0, s1, s2, s3);
-                    nz[3][i] = s1 * ab[3];
-                    nz[4][i] = s1 * ab[4];
-                    nz[1][i] = fmaf(s1, ab[1], s2 * fmaf(ab[3], 2.f * zx + zt, ab[4] * zt));
-                    nz[2][i] = fmaf(s1, ab[2], s2 * fmaf(ab[3], zx, ab[4] * (2.f * zt + zx)));
-                    nz[0][i] = s1 * ab[0] + s2 * (zx * ab[1] + zt * ab[2] + zq * ab[3] + zr * ab[4])
-                             + s3 * (ab[3] * zx * (zx + zt) + ab[4] * zt * (zt + zx));
+                    __syncthreads();                  // A / B are rewritten by the next (lower) layer
                 }
-                for (int i = 0; i < wi; ++i)
+            }
+        }   // tiles
+
+        // ---- combine the four warps' weight-gradient tiles (K split) into the block partial, fixed order
+        for (int w = 0; w < NG; ++w) {
+            if (warp == w) {
 #pragma unroll
-                    for (int c = 0; c < CH; ++c) zbar[c][i] = nz[c][i];
+                for (int l = 0; l < NH - 1; ++l) {
+                    const int wi = d.layers[l + 1], wo = d.layers[l + 2];
+#pragma unroll
+                    for (int a = 0; a < TJ; ++a)
+#pragma unroll
+                        for (int b = 0; b < TI; ++b) {
+                            const int j = tjg * TJ + a, i = tig * TI + b;
+                            if (j < wo && i < wi) g_s[woff[l + 1] + j * wi + i] += wacc[l][a][b];
+                        }
+                }
+            }
+            __syncthreads();
+        }
+        if (warp == 0) {
+            for (int off = 16; off; off >>= 1) {
+                lossR += __shfl_xor_sync(0xffffffffu, lossR, off);
+                lossI1 += __shfl_xor_sync(0xffffffffu, lossI1, off);
+                lossI2 += __shfl_xor_sync(0xffffffffu, lossI2, off);
+                lossB += __shfl_xor_sync(0xffffffffu, lossB, off);
             }
         }
-
-        // ---- publish this warp's partials
-        for (int off = 16; off; off >>= 1) {
-            lossR += __shfl_xor_sync(0xffffffffu, lossR, off);
-            lossI1 += __shfl_xor_sync(0xffffffffu, lossI1, off);
-            lossI2 += __shfl_xor_sync(0xffffffffu, lossI2, off);
-            lossB += __shfl_xor_sync(0xffffffffu, lossB, off);
-        }
-        __syncwarp();
-        if (gwarp < d.n_partials) {
-            float *dst = d.partials + (size_t)gwarp * d.partial_stride;
-            for (int i = lane; i < P; i += 32) dst[i] = g_s[i];
-            if (lane == 0) { dst[P] = lossR; dst[P + 1] = lossI1; dst[P + 2] = lossI2; dst[P + 3] = lossB; }
+        if ((int)blockIdx.x < d.n_partials) {
+            float *dst = d.partials + (size_t)blockIdx.x * d.partial_stride;
+            for (int i = threadIdx.x; i < P; i += blockDim.x) dst[i] = g_s[i];
+            if (threadIdx.x == 0) { dst[P] = lossR; dst[P + 1] = lossI1; dst[P + 2] = lossI2; dst[P + 3] = lossB; }
         }
         grid.sync();
 
         // -------------------------------------------------------------- phase 2: reduce, tolerance, Adam
-        const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-        if (gtid == 0) {
+        // every block reduces the four loss sums itself (same order everywhere => the same stop decision
+        // on every block, no extra grid barrier)
+        if (warp == 0) {
             float s[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int w = 0; w < d.n_partials; ++w)
+            for (int w = lane; w < d.n_partials; w += 32)
+#pragma unroll
                 for (int k = 0; k < 4; ++k) s[k] += d.partials[(size_t)w * d.partial_stride + P + k];
-            float loss = s[0] * d.invR + s[1] * d.invI;
-            if (d.pde == 0) loss += s[2] * d.invI;
-            loss += s[3] * d.invB;
-            d.status[0] = loss;                                       // loss of the weights BEFORE this epoch's step
-            d.status[1] = __int_as_float(epoch);
-            if (d.loss_trace && d.trace_every > 0 && (epoch - 1) % d.trace_every == 0) d.loss_trace[(epoch - 1) / d.trace_every] = loss;
-            d.stop[0] = (d.tol >= 0.f && loss < d.tol) ? 1 : 0;       // B_train.py:84: break before the step
+            for (int off = 16; off; off >>= 1)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) s[k] += __shfl_xor_sync(0xffffffffu, s[k], off);
+            if (lane == 0) {
+                float loss = s[0] * d.invR + s[1] * d.invI;
+                if (d.pde == 0) loss += s[2] * d.invI;
+                loss += s[3] * d.invB;
+                U_s[0] = loss;
+                if (blockIdx.x == 0) {
+                    d.status[0] = loss;                                   // loss of the weights BEFORE this epoch's step
+                    d.status[1] = __int_as_float(epoch);
+                    if (d.loss_trace && d.trace_every > 0 && (epoch - 1) % d.trace_every == 0) d.loss_trace[(epoch - 1) / d.trace_every] = loss;
+                }
+            }
         }
-        grid.sync();
-        const bool stop = d.stop[0] != 0;
+        __syncthreads();
+        const bool stop = d.tol >= 0.f && U_s[0] < d.tol;                 // B_train.py:84: break before the step
         if (!stop) {
             const double bc1 = 1.0 - pow((double)d.beta1, (double)epoch);
             const double bc2 = 1.0 - pow((double)d.beta2, (double)epoch);
             const float step_size = (float)((double)d.lr / bc1);
             const float bc2_sqrt = (float)sqrt(bc2);
-            for (int i = gtid; i < P; i += gridDim.x * blockDim.x) {
-                float gsum = 0.f;
-                for (int w = 0; w < d.n_partials; ++w) gsum += d.partials[(size_t)w * d.partial_stride + i];
-                if (d.grad_out) d.grad_out[i] = gsum;
-                // torch.optim.Adam (single-tensor semantics)
-                const float m = d.adam_m[i] = d.adam_m[i] + (gsum - d.adam_m[i]) * d.omb1;     // exp_avg.lerp_(grad, 1 - beta1)
-                const float v = d.adam_v[i] = fmaf(d.omb2 * gsum, gsum, d.beta2 * d.adam_v[i]);   // mul_(beta2).addcmul_(g, g, 1 - beta2)
-                const float denom = sqrtf(v) / bc2_sqrt + d.eps;
-                d.params[i] = d.params[i] - step_size * (m / denom);
+            // gradient reduction: 8 lanes per parameter, fixed order (deterministic), then torch.optim.Adam
+            const int gthreads = gridDim.x * blockDim.x;
+            const int sub = threadIdx.x & 7;
+            const int gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, ngroups = gthreads >> 3;
+            for (int i0 = 0; i0 < P; i0 += ngroups) {                     // same trip count on every thread (shuffles below)
+                const int i = i0 + gid;
+                float gs = 0.f;
+                if (i < P)
+                    for (int w = sub; w < d.n_partials; w += 8) gs += d.partials[(size_t)w * d.partial_stride + i];
+                gs += __shfl_xor_sync(0xffffffffu, gs, 1);
+                gs += __shfl_xor_sync(0xffffffffu, gs, 2);
+                gs += __shfl_xor_sync(0xffffffffu, gs, 4);
+                if (sub == 0 && i < P) {
+                    if (d.grad_out) d.grad_out[i] = gs;
+                    const float m = d.adam_m[i] = d.adam_m[i] + (gs - d.adam_m[i]) * d.omb1;          // exp_avg.lerp_(grad, 1 - beta1)
+                    const float v = d.adam_v[i] = fmaf(d.omb2 * gs, gs, d.beta2 * d.adam_v[i]);        // mul_(beta2).addcmul_(g, g, 1 - beta2)
+                    const float denom = sqrtf(v) / bc2_sqrt + d.eps;
+                    d.params[i] = d.params[i] - step_size * (m / denom);
+                }
             }
         }
         grid.sync();
@@ -310,46 +458,62 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pinn_train_kernel(const PinnDes
     }
 }
 
-static void *pick_kernel(const PinnDesc &d, int *wmax)
+struct KernelPick { void *fn; int wmax, nh; };
+
+static KernelPick pick_kernel(const PinnDesc &d)
 {
+    const int nh = d.nlayers - 2;
     int maxw = 0;
-    for (int l = 0; l < d.nlayers; ++l) maxw = d.layers[l] > maxw ? d.layers[l] : maxw;
-    if (maxw <= 20) { *wmax = 20; return (void *)pinn_train_kernel<20>; }
-    if (maxw <= 40) { *wmax = 40; return (void *)pinn_train_kernel<40>; }
-    return nullptr;
+    for (int l = 1; l < d.nlayers - 1; ++l) maxw = d.layers[l] > maxw ? d.layers[l] : maxw;
+    if (maxw <= 20) {
+        if (nh == 1) return {(void *)pinn_train_kernel<20, 1>, 20, 1};
+        if (nh == 2) return {(void *)pinn_train_kernel<20, 2>, 20, 2};
+        if (nh == 3) return {(void *)pinn_train_kernel<20, 3>, 20, 3};
+        if (nh == 4) return {(void *)pinn_train_kernel<20, 4>, 20, 4};
+    } else if (maxw <= 40) {
+        if (nh == 1) return {(void *)pinn_train_kernel<40, 1>, 40, 1};
+        if (nh == 2) return {(void *)pinn_train_kernel<40, 2>, 40, 2};
+        if (nh == 3) return {(void *)pinn_train_kernel<40, 3>, 40, 3};
+    }
+    return {nullptr, 0, 0};
+}
+
+static size_t smem_bytes(const PinnDesc &d, const KernelPick &k)
+{
+    const int P4 = (d.n_params + 3) & ~3;
+    const int GJ = k.wmax / NG, GJP = (GJ + 3) & ~3;
+    const size_t fl = (size_t)2 * P4 + (size_t)2 * (k.nh - 1) * k.wmax * NG * GJP + (size_t)2 * k.wmax * (CH * PT + 1) + (size_t)NG * CH * PT + 8;
+    return fl * sizeof(float);
 }
 
 cudaError_t plan_pinn_train(const PinnDesc &d, int n_sm, int *blocks_out, size_t *smem_out, int *n_partials)
 {
-    int WMAX = 0;
-    void *kern = pick_kernel(d, &WMAX);
-    if (!kern) return cudaErrorInvalidValue;
-    const int P4 = (d.n_params + 3) & ~3;
-    const size_t smem = ((size_t)P4 + (size_t)WARPS * (P4 + 2 * 32 * WMAX + 8)) * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const KernelPick k = pick_kernel(d);
+    if (!k.fn) return cudaErrorInvalidValue;
+    const size_t smem = smem_bytes(d, k);
+    cudaError_t e = cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k.fn, NG * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
-    const int chunks = (d.NR + 31) / 32 + (d.NI + 31) / 32 + (d.NB + 31) / 32;
-    int blocks = (chunks + WARPS - 1) / WARPS;
+    const int tiles = (d.NR + PT - 1) / PT + (d.NI + PT - 1) / PT + (d.NB + PT - 1) / PT;
+    int blocks = tiles;
     if (blocks > n_sm * per_sm) blocks = n_sm * per_sm;
     if (blocks < 1) blocks = 1;
     *blocks_out = blocks;
     *smem_out = smem;
-    *n_partials = blocks * WARPS < chunks ? blocks * WARPS : chunks;
+    *n_partials = blocks;
     return cudaSuccess;
 }
 
 cudaError_t launch_pinn_train(const PinnDesc &d, int blocks, size_t smem, cudaStream_t st)
 {
-    int WMAX = 0;
-    void *kern = pick_kernel(d, &WMAX);
-    if (!kern) return cudaErrorInvalidValue;
+    const KernelPick k = pick_kernel(d);
+    if (!k.fn) return cudaErrorInvalidValue;
     PinnDesc dd = d;
     void *args[] = {&dd};
-    return cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(WARPS * 32), args, smem, st);
+    return cudaLaunchCooperativeKernel(k.fn, dim3(blocks), dim3(NG * 32), args, smem, st);
 }
 
 }  // namespace gp
