@@ -248,9 +248,14 @@ static int make_plan(std::vector<ParamRow> &rows, int pde, int n, int n_sm, cons
     double best = 1e300;
     int bM = 0, bSL = 0, bW = 0, bPriv = 0;
     std::vector<Chunk> bestChunks, ch;
+    int maxS = 1;
+    for (int g = 0; g < plan.groups; ++g) maxS = std::max(maxS, gstart[g + 1] - gstart[g]);
+    int Mcap = 5;                                       // parameters per thread beyond the largest sibling group only idle
+    for (int mi = 3; mi >= 0; --mi) if (Ms[mi] >= maxS) { Mcap = Ms[mi]; break; }
     for (int mi = 0; mi < 4; ++mi) {
         const int M = Ms[mi];
         if (a->cfg_M > 0 && M != a->cfg_M) continue;
+        if (a->cfg_M == 0 && M > Mcap) continue;
         const int maxw = maxw_for_m(M);
         // ---- private rings: dynamic tickets, mixed item sizes ----
         if (mode != 1) {

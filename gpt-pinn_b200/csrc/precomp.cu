@@ -87,6 +87,168 @@ __global__ void __launch_bounds__(128) mlp_channels_kernel(const MlpDesc d, cons
         if (o.ptr[c]) o.ptr[c][p * o.ld[c]] = a[c][0];
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Tiled variant for the narrow PINNs (hidden width <= 40: Klein-Gordon [2,40,40,1], Burgers [2,20,20,20,20,1]).
+// Block = 4 warps = 4 neuron groups, tile = 32 points (lane = point).  A thread keeps the channels of its own
+// neurons in registers; the previous layer's activations of all neurons are staged in shared memory and each
+// layer is a small GEMM whose weights are read as warp-wide float4 broadcasts (same structure as the forward
+// half of pinn_train.cu).  Persistent over tiles; weights are loaded into shared memory once per block.
+// ---------------------------------------------------------------------------------------------------
+constexpr int TNG = 4, TPT = 32;
+
+template <int CHN>
+__device__ __forceinline__ void tile_act(int act, const float (&z)[CHN], float (&a)[CHN])
+{
+    float s0, s1, s2;
+    if (act == 0) { float sn, cs; sincosf(z[0], &sn, &cs); s0 = cs; s1 = -sn; s2 = -cs; }
+    else { s0 = tanhf(z[0]); s1 = 1.f - s0 * s0; s2 = -2.f * s0 * s1; }
+    a[0] = s0;
+    if constexpr (CHN >= 3) { a[1] = s1 * z[1]; a[2] = s1 * z[2]; }
+    if constexpr (CHN >= 5) {
+        a[3] = fmaf(s2 * z[1], z[1] + z[2], s1 * z[3]);
+        a[4] = fmaf(s2 * z[2], z[2] + z[1], s1 * z[4]);
+    }
+}
+
+template <int WMAX, int NH, int CHN>
+__global__ void __launch_bounds__(TNG * 32, 4) mlp_channels_tile_kernel(const MlpDesc d, const float *__restrict__ xt, long long N, const MlpOut o)
+{
+    constexpr int GJ = WMAX / TNG, GJP = (GJ + 3) & ~3;
+    constexpr int NS = CHN * TPT + 1;
+    extern __shared__ __align__(16) float sm[];
+    int woff[NH + 1], boff[NH + 1], P = 0;
+#pragma unroll
+    for (int l = 0; l <= NH; ++l) { woff[l] = P; P += d.layers[l] * d.layers[l + 1]; boff[l] = P; P += d.layers[l + 1]; }
+    const int P4 = (P + 3) & ~3;
+    float *w_s = sm;
+    float *wt_s = w_s + P4;                                   // [NH-1][WMAX][TNG][GJP]
+    float *A_s = wt_s + (NH - 1) * WMAX * TNG * GJP;          // [WMAX][NS]
+    float *U_s = A_s + WMAX * NS;                             // [TNG][CHN][TPT]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, j0 = warp * GJ;
+#pragma unroll
+    for (int l = 0; l <= NH; ++l) {
+        const int nw = d.layers[l] * d.layers[l + 1];
+        for (int i = threadIdx.x; i < nw; i += blockDim.x) w_s[woff[l] + i] = d.W[l][i];
+        for (int i = threadIdx.x; i < d.layers[l + 1]; i += blockDim.x) w_s[boff[l] + i] = d.b[l][i];
+    }
+    __syncthreads();
+    for (int l = 1; l < NH; ++l) {
+        const float *W = w_s + woff[l];
+        const int wi = d.layers[l], wo = d.layers[l + 1];
+        float *wt = wt_s + (l - 1) * WMAX * TNG * GJP;
+        for (int e = threadIdx.x; e < WMAX * TNG * GJP; e += blockDim.x) {
+            const int a = e / (TNG * GJP), g = (e / GJP) % TNG, s = e % GJP, b = g * GJ + s;
+            wt[e] = (s < GJ && b < wo && a < wi) ? W[b * wi + a] : 0.f;
+        }
+    }
+    __syncthreads();
+    const long long ntiles = (N + TPT - 1) / TPT;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long p = tile * TPT + lane;
+        const bool live = p < N;
+        const float x = live ? xt[2 * p] : 0.f, t = live ? xt[2 * p + 1] : 0.f;
+        float z[CHN][GJ];
+        {
+            const float *W = w_s + woff[0], *Bv = w_s + boff[0];
+#pragma unroll
+            for (int jj = 0; jj < GJ; ++jj) {
+                const int j = j0 + jj;
+                const bool ok = j < d.layers[1];
+                const float wx = ok ? W[j * 2] : 0.f, w1 = ok ? W[j * 2 + 1] : 0.f;
+                z[0][jj] = ok ? fmaf(wx, x, fmaf(w1, t, Bv[j])) : 0.f;
+                if constexpr (CHN >= 3) { z[1][jj] = wx; z[2][jj] = w1; }
+                if constexpr (CHN >= 5) { z[3][jj] = 0.f; z[4][jj] = 0.f; }
+            }
+        }
+#pragma unroll
+        for (int l = 0; l < NH; ++l) {
+#pragma unroll
+            for (int jj = 0; jj < GJ; ++jj) {
+                float zz[CHN], aa[CHN];
+#pragma unroll
+                for (int c = 0; c < CHN; ++c) zz[c] = z[c][jj];
+                tile_act<CHN>(d.act, zz, aa);
+                const bool ok = (j0 + jj) < d.layers[l + 1];
+#pragma unroll
+                for (int c = 0; c < CHN; ++c) A_s[(j0 + jj) * NS + c * TPT + lane] = ok ? aa[c] : 0.f;
+            }
+            __syncthreads();
+            if (l < NH - 1) {
+                const float *wt = wt_s + l * WMAX * TNG * GJP + warp * GJP;
+                const float *Bv = w_s + boff[l + 1];
+#pragma unroll
+                for (int jj = 0; jj < GJ; ++jj) {
+                    z[0][jj] = (j0 + jj) < d.layers[l + 2] ? Bv[j0 + jj] : 0.f;
+#pragma unroll
+                    for (int c = 1; c < CHN; ++c) z[c][jj] = 0.f;
+                }
+                const int wi = d.layers[l + 1];
+                for (int i = 0; i < wi; ++i) {
+                    float av[CHN], wv[GJP];
+#pragma unroll
+                    for (int c = 0; c < CHN; ++c) av[c] = A_s[i * NS + c * TPT + lane];
+#pragma unroll
+                    for (int s = 0; s < GJP; s += 4) {
+                        const float4 w4 = *reinterpret_cast<const float4 *>(wt + i * TNG * GJP + s);
+                        wv[s] = w4.x; wv[s + 1] = w4.y; wv[s + 2] = w4.z; wv[s + 3] = w4.w;
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < GJ; ++jj)
+#pragma unroll
+                        for (int c = 0; c < CHN; ++c) z[c][jj] = fmaf(wv[jj], av[c], z[c][jj]);
+                }
+                __syncthreads();
+            }
+        }
+        {
+            const float *W = w_s + woff[NH];
+            float pu[CHN];
+#pragma unroll
+            for (int c = 0; c < CHN; ++c) pu[c] = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < GJ; ++jj) {
+                const float wv = (j0 + jj) < d.layers[NH] ? W[j0 + jj] : 0.f;
+#pragma unroll
+                for (int c = 0; c < CHN; ++c) pu[c] = fmaf(wv, A_s[(j0 + jj) * NS + c * TPT + lane], pu[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < CHN; ++c) U_s[(warp * CHN + c) * TPT + lane] = pu[c];
+            __syncthreads();
+            if (warp == 0 && live) {
+#pragma unroll
+                for (int c = 0; c < CHN; ++c) {
+                    float s = c == 0 ? w_s[boff[NH]] : 0.f;
+#pragma unroll
+                    for (int g = 0; g < TNG; ++g) s += U_s[(g * CHN + c) * TPT + lane];
+                    if (o.ptr[c]) o.ptr[c][p * o.ld[c]] = s;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <int WMAX, int NH>
+static cudaError_t launch_tile(const MlpDesc &d, const float *xt, long long N, const MlpOut &o, int ch, cudaStream_t st)
+{
+    constexpr int GJ = WMAX / TNG, GJP = (GJ + 3) & ~3;
+    int P = 0;
+    for (int l = 0; l <= NH; ++l) P += d.layers[l] * d.layers[l + 1] + d.layers[l + 1];
+    const size_t smem = ((size_t)((P + 3) & ~3) + (size_t)(NH - 1) * WMAX * TNG * GJP + (size_t)WMAX * (ch * TPT + 1) + (size_t)TNG * ch * TPT + 8) * sizeof(float);
+    void *kern = ch == 1 ? (void *)mlp_channels_tile_kernel<WMAX, NH, 1> : (ch == 3 ? (void *)mlp_channels_tile_kernel<WMAX, NH, 3> : (void *)mlp_channels_tile_kernel<WMAX, NH, 5>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, nsm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const long long ntiles = (N + TPT - 1) / TPT;
+    const unsigned blocks = (unsigned)(ntiles < 4LL * nsm ? ntiles : 4LL * nsm);
+    MlpDesc dd = d; MlpOut oo = o; const float *x2 = xt; long long n2 = N;
+    void *args[] = {&dd, &x2, &n2, &oo};
+    return cudaLaunchKernel(kern, dim3(blocks), dim3(TNG * 32), args, smem, st);
+}
+
 template <int WMAX>
 static cudaError_t launch_w(const MlpDesc &d, const float *xt, long long N, const MlpOut &o, int ch, size_t smem, cudaStream_t st)
 {
@@ -119,6 +281,19 @@ cudaError_t launch_mlp_channels(const MlpDesc &d, const float *xt, long long N, 
     const size_t smem = fl * sizeof(float);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     const int ch = (o.ptr[3] || o.ptr[4]) ? 5 : ((o.ptr[1] || o.ptr[2]) ? 3 : 1);
+    const int nh = d.nlayers - 2;
+    int maxh = 0;
+    for (int l = 1; l < d.nlayers - 1; ++l) maxh = d.layers[l] > maxh ? d.layers[l] : maxh;
+    if (nh >= 1 && maxh <= 20 && maxh % 4 == 0) {
+        if (nh == 1) return launch_tile<20, 1>(d, xt, N, o, ch, st);
+        if (nh == 2) return launch_tile<20, 2>(d, xt, N, o, ch, st);
+        if (nh == 3) return launch_tile<20, 3>(d, xt, N, o, ch, st);
+        if (nh == 4) return launch_tile<20, 4>(d, xt, N, o, ch, st);
+    } else if (nh >= 1 && maxh <= 40 && nh <= 3) {
+        if (nh == 1) return launch_tile<40, 1>(d, xt, N, o, ch, st);
+        if (nh == 2) return launch_tile<40, 2>(d, xt, N, o, ch, st);
+        if (nh == 3) return launch_tile<40, 3>(d, xt, N, o, ch, st);
+    }
     if (maxw <= 20) return launch_w<20>(d, xt, N, o, ch, smem, st);
     if (maxw <= 40) return launch_w<40>(d, xt, N, o, ch, smem, st);
     if (maxw <= 64) return launch_w<64>(d, xt, N, o, ch, smem, st);
