@@ -11,7 +11,7 @@ import torch
 
 from B_models import NN
 from B_train import initial_coefficients
-from _common import offline, sweep
+from _common import offline, pinn, sweep
 
 device = torch.device("cuda")
 
@@ -52,42 +52,44 @@ def gpt_test_loss(nu_train, xt_size, IC_size, BC_size, IC_u, BC_u, out,
 
 def pinn_test(b_test, layers_pinn, xt_resid, IC_xt, IC_u, BC_xt, BC_u, f_hat,
               epochs_pinn, lr_pinn, xt_test, tol):
-    times = np.zeros(len(b_test))
-    pinn_soln = np.zeros((xt_test.shape[0], len(b_test)))
-    for i, nu in enumerate(b_test):
-        t_start = time.time()
+    """One tolerance-stopped full PINN per test parameter (B_test.py:116-149), fused training kernel;
+    under torch.distributed each rank trains a contiguous block of the parameters."""
+    b_test = np.asarray(b_test, dtype=np.float64).reshape(-1)
+    t0 = time.time()
+    lo, hi = offline.shard_bounds(len(b_test))
+    local = torch.zeros((hi - lo, xt_test.shape[0]), dtype=torch.float32, device=xt_test.device)
+    for k, nu in enumerate(b_test[lo:hi]):
         PINN = NN(layers_pinn, nu).to(device)
-        optimizer = torch.optim.Adam(PINN.parameters(), lr=lr_pinn)
-        for j in range(1, epochs_pinn + 1):
-            loss = PINN.loss(xt_resid, IC_xt, IC_u, BC_xt, BC_u, f_hat)
-            if loss < tol:
-                break
-            optimizer.zero_grad()
-            loss.backward()
-            optimizer.step()
+        pinn.train_fused(PINN, "burgers", (nu,), xt_resid, f_hat, IC_xt, IC_u, None, BC_xt, BC_u,
+                         epochs_pinn, lr_pinn, tol=tol)
         with torch.no_grad():
-            soln = PINN(xt_test)
-        dt = (time.time() - t_start) / 3600
-        times[i] = dt if i == 0 else dt + times[i - 1]
-        pinn_soln[:, i][:, None] = soln.detach().cpu().numpy()
-    return times, pinn_soln
+            local[k] = PINN(xt_test)[:, 0]
+    pinn_soln = offline.gather_rows(local, len(b_test)).t().cpu().numpy().astype(np.float64)
+    return offline.spread_hours(time.time() - t0, len(b_test)), pinn_soln
 
 
 def pinn_test_loss(b_test, layers_pinn, xt_resid, IC_xt, IC_u, BC_xt, BC_u,
                    f_hat, epochs_pinn, lr_pinn, tol):
-    losses = np.zeros((61, len(b_test)))
-    for i, nu in enumerate(b_test):
+    """B_test.py:154-181: losses[0] = initial loss; losses[j/1000] = the loss evaluated at the top of
+    iteration j (after j-1 steps) for j % 1000 == 0 or j == epochs; on the tolerance break the stopping
+    loss goes into the first still-zero slot."""
+    b_test = np.asarray(b_test, dtype=np.float64).reshape(-1)
+    lo, hi = offline.shard_bounds(len(b_test))
+    local = np.zeros((hi - lo, 61))
+    for k, nu in enumerate(b_test[lo:hi]):
         PINN = NN(layers_pinn, nu).to(device)
-        optimizer = torch.optim.Adam(PINN.parameters(), lr=lr_pinn)
-        losses[0, i] = PINN.loss(xt_resid, IC_xt, IC_u, BC_xt, BC_u, f_hat).item()
-        for j in range(1, epochs_pinn + 1):
-            loss = PINN.loss(xt_resid, IC_xt, IC_u, BC_xt, BC_u, f_hat)
+        r = pinn.train_fused(PINN, "burgers", (nu,), xt_resid, f_hat, IC_xt, IC_u, None, BC_xt, BC_u,
+                             epochs_pinn, lr_pinn, tol=tol, trace_every=1)
+        done = pinn.epochs_done(r)                                   # iterations entered
+        tr = r["trace"].cpu().numpy().astype(np.float64)             # tr[j-1] = loss at the top of iteration j
+        col = local[k]
+        if done >= 1:
+            col[0] = tr[0]
+        stopped = tol is not None and done >= 1 and tr[done - 1] < tol
+        for j in range(1, done + 1):
             if (j % 1000 == 0) or (j == epochs_pinn):
-                losses[int(j / 1000), i] = loss.item()
-            if loss < tol:
-                losses[np.where(losses[:, i] == 0)[0][0], i] = loss.item()
-                break
-            optimizer.zero_grad()
-            loss.backward()
-            optimizer.step()
-    return losses
+                col[int(j / 1000)] = tr[j - 1]
+        if stopped:
+            col[np.where(col == 0)[0][0]] = tr[done - 1]
+    out = offline.gather_rows(torch.from_numpy(local).to(xt_resid.device), len(b_test))
+    return out.t().cpu().numpy().astype(np.float64)

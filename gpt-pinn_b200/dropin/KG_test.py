@@ -49,32 +49,38 @@ def gpt_test_loss(kg_test, out, out_xx, out_tt, out_IC, out_IC_t, out_BC, fhat,
 
 def pinn_test(kg_test, layers_pinn, xcos_x2cos2, xt_resid, IC_xt, IC_u1, IC_u2,
               BC_xt, BC_u, f_hat, epochs_pinn, lr_pinn, xt_test):
-    times = np.zeros(len(kg_test))
-    pinn_soln = np.zeros((xt_test.shape[0], len(kg_test)))
-    for i, (alpha, beta, gamma) in enumerate(kg_test):
-        t_start = time.time()
+    """One full PINN per test parameter (KG_test.py:81-111); the parameters are independent, so under
+    torch.distributed each rank trains a contiguous block of them and the solutions are all-gathered."""
+    kg_test = np.asarray(kg_test, dtype=np.float64).reshape(-1, 3)
+    t0 = time.time()
+    lo, hi = offline.shard_bounds(len(kg_test))
+    local = torch.zeros((hi - lo, xt_test.shape[0]), dtype=torch.float32, device=xt_test.device)
+    for k, (alpha, beta, gamma) in enumerate(kg_test[lo:hi]):
         PINN = NN(layers_pinn, alpha, beta, gamma, xcos_x2cos2).to(device)
         pinn.train_fused(PINN, "kg", (alpha, beta, gamma), xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u,
                          epochs_pinn, lr_pinn, xcos=xcos_x2cos2)
         with torch.no_grad():
-            soln = PINN(xt_test)
-        dt = (time.time() - t_start) / 3600
-        times[i] = dt if i == 0 else dt + times[i - 1]
-        pinn_soln[:, i][:, None] = soln.detach().cpu().numpy()
+            local[k] = PINN(xt_test)[:, 0]
+    soln = offline.gather_rows(local, len(kg_test))
+    pinn_soln = soln.t().cpu().numpy().astype(np.float64)
+    times = offline.spread_hours(time.time() - t0, len(kg_test))
     return times, pinn_soln
 
 
 def pinn_test_loss(kg_test, layers_pinn, xcos_x2cos2, xt_resid, IC_xt, IC_u1,
                    IC_u2, BC_xt, BC_u, f_hat, epochs_pinn, lr_pinn):
-    losses = np.zeros((101, len(kg_test)))
-    for i, (alpha, beta, gamma) in enumerate(kg_test):
+    """Loss after 0, 1000, 2000, ... steps and after the last step (KG_test.py:116-140), sharded like pinn_test."""
+    kg_test = np.asarray(kg_test, dtype=np.float64).reshape(-1, 3)
+    lo, hi = offline.shard_bounds(len(kg_test))
+    local = torch.zeros((hi - lo, 101), dtype=torch.float32, device=xt_resid.device)
+    for k, (alpha, beta, gamma) in enumerate(kg_test[lo:hi]):
         PINN = NN(layers_pinn, alpha, beta, gamma, xcos_x2cos2).to(device)
-        # loss before the step of epochs 1, 1001, 2001, ... == loss after 0, 1000, 2000, ... steps (KG_test.py:125-139)
+        # loss before the step of epochs 1, 1001, 2001, ... == loss after 0, 1000, 2000, ... steps
         r = pinn.train_fused(PINN, "kg", (alpha, beta, gamma), xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u,
                              epochs_pinn, lr_pinn, xcos=xcos_x2cos2, trace_every=1000)
-        tr = r["trace"].cpu().numpy()
-        losses[:min(101, len(tr)), i] = tr[:101]
-        with torch.enable_grad():
-            final = PINN.loss(xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u).item()
-        losses[int(epochs_pinn / 1000), i] = final
-    return losses
+        tr = r["trace"]
+        local[k, :min(101, tr.numel())] = tr[:101]
+        final = pinn.train_fused(PINN, "kg", (alpha, beta, gamma), xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u,
+                                 1, 0.0, xcos=xcos_x2cos2)["loss"]          # lr = 0: evaluates the loss, leaves the weights
+        local[k, min(100, int(epochs_pinn / 1000))] = final
+    return offline.gather_rows(local, len(kg_test)).t().cpu().numpy().astype(np.float64)

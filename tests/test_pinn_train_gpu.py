@@ -138,3 +138,46 @@ def test_dropin_pinn_train_prints_and_updates(capsys):
     KG_train.pinn_train(net, *params, xt.requires_grad_(), IC_xt.requires_grad_(), IC_u1, IC_u2, BC_xt, BC_u, f_hat, 30, 5e-4)
     assert "PINN Final Loss:" in capsys.readouterr().out
     assert not torch.equal(_pack_params(net), p0)
+
+
+def test_dropin_pinn_test_sweeps_shapes_and_first_records():
+    """KG_test.pinn_test / pinn_test_loss and B_test.pinn_test_loss on the fused kernel: shapes, the
+    record layout of the reference loops, and the recorded losses against a torch replay."""
+    import B_data
+    import B_models
+    import B_test
+    import KG_test
+    make, params, t, xcos = _kg_setup(nc=9, ic=16, bc=16, seed=21)
+    xt, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u = t
+    kg_test = np.array([[-1.2, 0.3, 0.6], [-1.7, 0.9, 0.1]])
+    xt_test = xt[:50].contiguous()
+    times, soln = KG_test.pinn_test(kg_test, np.array([2, 40, 40, 1]), xcos, xt, IC_xt, IC_u1, IC_u2, BC_xt, BC_u, f_hat,
+                                    40, 5e-4, xt_test)
+    assert soln.shape == (50, 2) and times.shape == (2,) and np.isfinite(soln).all()
+    losses = KG_test.pinn_test_loss(kg_test, np.array([2, 40, 40, 1]), xcos, xt, IC_xt, IC_u1, IC_u2, BC_xt, BC_u, f_hat,
+                                    1500, 5e-4)
+    assert losses.shape == (101, 2)
+    assert (losses[0] > 0).all() and (losses[1] > 0).all() and (losses[2:] == 0).all()
+    assert (losses[1] < losses[0]).all()                       # training made progress; slot 1 = after 1000 (then 1500) steps
+    # Burgers: replay with torch and compare the recorded values
+    xtb, fb, _ = B_data.residual_data(-1.0, 1.0, 0.0, 1.0, 11, 4)
+    ICx, ICu, BCx, BCu = B_data.ICBC_data(-1.0, 1.0, 0.0, 1.0, 12, 12)
+    xtb, fb, ICx, ICu, BCx, BCu = (a.cuda() for a in (xtb, fb, ICx, ICu, BCx, BCu))
+    layers = np.array([2, 20, 20, 20, 20, 1])
+    got = B_test.pinn_test_loss(np.array([0.3]), layers, xtb, ICx, ICu, BCx, BCu, fb, 1000, 2e-3, 1e-9)
+    ref = B_models.NN(layers, 0.3).cuda()
+    opt = torch.optim.Adam(ref.parameters(), lr=2e-3)
+    xr = xtb.clone().requires_grad_()
+    want0 = want1000 = None
+    for j in range(1, 1001):
+        loss = ref.loss(xr, ICx, ICu, BCx, BCu, fb)
+        if j == 1:
+            want0 = float(loss)
+        if j == 1000:
+            want1000 = float(loss)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    assert got.shape == (61, 1)
+    assert abs(got[0, 0] - want0) <= 1e-5 * want0
+    assert abs(got[1, 0] - want1000) <= 5e-2 * want1000        # 1000 Adam steps in fp32: trajectories agree to a few percent
