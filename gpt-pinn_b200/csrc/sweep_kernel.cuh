@@ -28,6 +28,9 @@
 #ifndef GP_FWD_VARIANT
 #define GP_FWD_VARIANT 0
 #endif
+#ifndef GP_REGT_MAX_SL
+#define GP_REGT_MAX_SL 2
+#endif
 #ifndef GP_PHASE_SYNC
 #define GP_PHASE_SYNC 0
 #endif
@@ -78,6 +81,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
     constexpr int VEC0 = TR::NARR * ARR, VEC1 = VEC0 + RT;
     constexpr int NST = PRIV ? NST_PRIV : NSTAGE;
     constexpr unsigned FULLM = 0xffffffffu;
+    constexpr int REGT_MAX_SL = GP_REGT_MAX_SL;   // items with at most this many sibling lanes build T rows in registers
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -197,7 +201,77 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
             // ------------------------------ segment 0: PDE residual rows ------------------
             for (int t = 0; t < p.ntile[0]; ++t) {
                 const float *slot = acquire();
-                if (active) {
+                if (active && SL <= REGT_MAX_SL) {
+                    // ---- few sibling lanes: a T row is used by at most REGT_MAX_SL lanes, so staging the whole T block
+                    //      through shared memory costs more than it saves.  Each lane forms the T quads of its own row in
+                    //      registers (fused multiply-adds: within one ulp of the reference's separately rounded T).
+                    const float *Pblk = slot + (PDE == PDE_B ? 3 : 2) * ARR;
+                    const int fhoff = (PDE == PDE_KG) ? VEC1 : VEC0;
+                    auto quads = [&](int rr, int q, float *Tq, float *Pq, float *Xq) {
+                        const int o = q * QS + rr * 4;
+                        float4 tv = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (q < NQ) {
+                            const float4 a = ld4(slot + o), b = ld4(slot + ARR + o);
+                            if constexpr (PDE == PDE_B) {
+                                const float4 xq = ld4(slot + 2 * ARR + o), pq = ld4(Pblk + o);
+                                tv.x = fmaf(it.tp0, b.x, a.x); tv.y = fmaf(it.tp0, b.y, a.y);
+                                tv.z = fmaf(it.tp0, b.z, a.z); tv.w = fmaf(it.tp0, b.w, a.w);
+                                Xq[4 * q] = xq.x; Xq[4 * q + 1] = xq.y; Xq[4 * q + 2] = xq.z; Xq[4 * q + 3] = xq.w;
+                                Pq[4 * q] = pq.x; Pq[4 * q + 1] = pq.y; Pq[4 * q + 2] = pq.z; Pq[4 * q + 3] = pq.w;
+                            } else {
+                                const float4 d = ld4(Pblk + o);
+                                tv.x = fmaf(it.tp1, d.x, fmaf(it.tp0, b.x, a.x)); tv.y = fmaf(it.tp1, d.y, fmaf(it.tp0, b.y, a.y));
+                                tv.z = fmaf(it.tp1, d.z, fmaf(it.tp0, b.z, a.z)); tv.w = fmaf(it.tp1, d.w, fmaf(it.tp0, b.w, a.w));
+                                Pq[4 * q] = d.x; Pq[4 * q + 1] = d.y; Pq[4 * q + 2] = d.z; Pq[4 * q + 3] = d.w;
+                            }
+                        }
+                        if (q == N / 4) {
+                            float fc = 0.f;
+                            if constexpr (PDE == PDE_KG) { fc = slot[VEC0 + rr]; if (has_fhat) fc -= slot[VEC1 + rr]; }
+                            else { if (has_fhat) fc = -slot[VEC0 + rr]; }
+                            set_comp(tv, N % 4, fc);
+                        }
+                        Tq[4 * q] = tv.x; Tq[4 * q + 1] = tv.y; Tq[4 * q + 2] = tv.z; Tq[4 * q + 3] = tv.w;
+                    };
+                    int r = slice;
+                    float Tv[4 * NQT], Pv[4 * NQ], Xv[PDE == PDE_B ? 4 * NQ : 1];
+#pragma unroll
+                    for (int q = 0; q < NQT; ++q) quads(r, q, Tv, Pv, Xv);
+                    float fh = 0.f;
+                    if (has_fhat) fh = slot[fhoff + r];
+                    for (; r < RT; r += RL) {
+                        const int rn = min(r + RL, RT - 1);
+                        float first[M], w2[M], w3[M];
+#pragma unroll
+                        for (int m = 0; m < M; ++m) {
+                            const float u = dotn<N>(Pv, c[m], 0.f);
+                            float d, nl;
+                            if constexpr (PDE == PDE_KG) { d = dotn<N>(Tv, c[m], fmaf(sp0[m], u * u, Tv[N])); nl = sp1[m] * u; w3[m] = 0.f; }
+                            else if constexpr (PDE == PDE_AC) { const float u2 = u * u; d = dotn<N>(Tv, c[m], fmaf(sp0[m], u2 * u, Tv[N])); nl = sp1[m] * u2; w3[m] = 0.f; }
+                            else { const float ux = dotn<N>(Xv, c[m], 0.f); d = dotn<N>(Tv, c[m], fmaf(u, ux, Tv[N])); nl = ux; w3[m] = u; }
+                            lacc[m] = fmaf(d, d, lacc[m]);
+                            first[m] = has_fhat ? d + fh : d;
+                            w2[m] = first[m] * nl;                 // weight of P[k]
+                            w3[m] = first[m] * w3[m];              // Burgers: weight of P_x[k]
+                        }
+                        if (has_fhat) fh = slot[fhoff + rn];
+#pragma unroll
+                        for (int q = 0; q < NQT; ++q) {
+#pragma unroll
+                            for (int m = 0; m < M; ++m)
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk) {
+                                    const int k = 4 * q + kk;
+                                    if (k < N) {
+                                        g[m][k] = fmaf(first[m], Tv[k], g[m][k]);
+                                        g[m][k] = fmaf(w2[m], Pv[k], g[m][k]);
+                                        if constexpr (PDE == PDE_B) g[m][k] = fmaf(w3[m], Xv[k], g[m][k]);
+                                    }
+                                }
+                            quads(rn, q, Tv, Pv, Xv);
+                        }
+                    }
+                } else if (active) {
                     // ---- per-warp T block (bit-identical to the reference's T tensor) -----
                     for (int e = lane; e < NQT * RT; e += 32) {
                         const int q = e / RT, r = e % RT;
