@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "../../include/gptpinn_b200.h"
@@ -147,19 +148,32 @@ static double smsp_eff(double warps_per_smsp)
 }
 static const double kL2BytesPerCycle = 2200.0;       // chip-wide L2 -> SM budget the planner allows itself
 
-// makespan of `t` (already in hand-out order) on `workers` identical workers, greedy (= ticket order)
+// makespan of items handed out in list order (= ticket order) to `workers` identical workers, each item going to
+// the worker that frees up first.  Item times come in a few size classes, so worker loads are kept as a
+// (load -> number of workers) map and whole runs of equal items are assigned at once.
 static double makespan(const std::vector<double> &t, int workers)
 {
     if (t.empty()) return 0.0;
-    std::vector<double> heap((size_t)std::min<size_t>(workers, t.size()), 0.0);   // min-heap of finish times
-    auto cmp = [](double x, double y) { return x > y; };
+    std::map<double, long long> loads;
+    loads[0.0] = workers;
     double mx = 0.0;
-    for (double d : t) {
-        std::pop_heap(heap.begin(), heap.end(), cmp);
-        double f = heap.back() + d;
-        heap.back() = f;
-        std::push_heap(heap.begin(), heap.end(), cmp);
-        if (f > mx) mx = f;
+    size_t i = 0;
+    while (i < t.size()) {
+        size_t j = i;
+        while (j < t.size() && t[j] == t[i]) ++j;          // run of equal item times
+        long long n = (long long)(j - i);
+        const double s = t[i];
+        while (n > 0) {
+            auto it = loads.begin();                        // least-loaded workers
+            const double L = it->first;
+            const long long k = it->second;
+            const long long m = n < k ? n : k;
+            if (m == k) loads.erase(it); else it->second = k - m;
+            loads[L + s] += m;
+            if (L + s > mx) mx = L + s;
+            n -= m;
+        }
+        i = j;
     }
     return mx;
 }
@@ -264,22 +278,24 @@ static int make_plan(std::vector<ParamRow> &rows, int pde, int n, int n_sm, cons
         if (mode != 1) {
             const int wsmem = (int)((227.0 * 1024 - 64) / (NST_PRIV * slot_p + (n / 4 + 1) * 4 * RT_PRIV * 4 + NST_PRIV * 8));
             const int maxwp = std::max(1, std::min(maxw, wsmem));
-            for (int W = maxwp; W >= 1; --W) {
-                if (a->cfg_W > 0 && W != std::min(a->cfg_W, maxwp)) continue;
-                if (a->cfg_W == 0 && W < maxwp - 3) break;                 // fewer resident warps never paid off in practice
-                const int workers = n_sm * W;
-                for (int cap = 32; cap >= 1; cap >>= 1) {
-                    if (a->cfg_SL > 0) {
-                        if (cap != 32) break;
-                        ch.clear();
-                        for (int g = 0; g < plan.groups; ++g)
-                            for (int s0 = 0, S = gstart[g + 1] - gstart[g]; s0 < S; s0 += a->cfg_SL * M)
-                                ch.push_back({g, s0, std::min(S - s0, a->cfg_SL * M), a->cfg_SL});
-                    } else {
-                        decompose(gstart, M, cap, ch);
-                        if (cap < 32 && !ch.empty() && ch.front().SL < cap) break;     // the cap no longer binds
-                        refine_tail(ch, M, workers, pde, n, tiles_p, RT_PRIV);
-                    }
+            for (int cap = 32; cap >= 1; cap >>= 1) {
+                std::vector<Chunk> base;
+                if (a->cfg_SL > 0) {
+                    if (cap != 32) break;
+                    for (int g = 0; g < plan.groups; ++g)
+                        for (int s0 = 0, S = gstart[g + 1] - gstart[g]; s0 < S; s0 += a->cfg_SL * M)
+                            base.push_back({g, s0, std::min(S - s0, a->cfg_SL * M), a->cfg_SL});
+                } else {
+                    decompose(gstart, M, cap, base);
+                    if (cap < 32 && !base.empty() && base.front().SL < cap) continue;  // the cap does not bind: same as the previous one
+                    if ((long long)base.size() > 12LL * n_sm * maxwp) break;           // finer than 12 items per resident warp never pays
+                }
+                // with at least one item per resident warp the full warp count is always best
+                const int wlo = (a->cfg_W == 0 && (long long)base.size() >= (long long)n_sm * maxwp) ? maxwp : std::max(1, maxwp - 3);
+                for (int W = maxwp; W >= wlo; --W) {
+                    if (a->cfg_W > 0 && W != std::min(a->cfg_W, maxwp)) continue;
+                    ch = base;
+                    if (a->cfg_SL == 0) refine_tail(ch, M, n_sm * W, pde, n, tiles_p, RT_PRIV);
                     std::vector<double> t(ch.size());
                     for (size_t i = 0; i < ch.size(); ++i) t[i] = item_instr(pde, n, M, ch[i].SL, 0, tiles_p, RT_PRIV);
                     const int Wuse = (int)std::max<long long>(1, std::min<long long>(W, ((long long)ch.size() + n_sm - 1) / n_sm));
@@ -300,8 +316,14 @@ static int make_plan(std::vector<ParamRow> &rows, int pde, int n, int n_sm, cons
                 for (int W = 1; W <= maxw; ++W) {
                     if (a->cfg_W > 0 && W != std::min(a->cfg_W, maxw)) continue;
                     const long long ctas = std::min<long long>(n_sm, (nit + W - 1) / W);
-                    const double rounds = (double)((nit + ctas * W - 1) / (ctas * W));
-                    const double issue = 1.2 * rounds * std::ceil(W / 4.0) * item_instr(pde, n, M, SL, 0, tiles_s, RT_SHARED) / smsp_eff(W / 4.0);
+                    const long long full_rounds = nit / (ctas * W), rest = nit - full_rounds * ctas * W;
+                    const double rounds = (double)(full_rounds + (rest > 0 ? 1 : 0));
+                    const double t_item = item_instr(pde, n, M, SL, 0, tiles_s, RT_SHARED);
+                    double issue = full_rounds * std::ceil(W / 4.0) * t_item / smsp_eff(W / 4.0);
+                    if (rest > 0) {                                         // the last round runs with fewer warps per SM
+                        const double wl = (double)((rest + ctas - 1) / ctas);
+                        issue += std::ceil(wl / 4.0) * t_item / smsp_eff(std::max(1.0, wl / 4.0));
+                    }
                     const double l2 = rounds * ctas * tiles_s * slot_s / kL2BytesPerCycle;
                     const double cst = std::max(issue, l2) * 1.02;          // ties go to the private rings
                     if (cst < best) { best = cst; bM = M; bSL = SL; bW = W; bPriv = 0; }
@@ -429,7 +451,7 @@ static int run_sweep(gptpinn_handle *h, int pde, int n, const Segments &seg, Pac
     const int NQT = n / 4 + 1;
     const size_t smem = plan.priv
         ? (size_t)plan.W * NST_PRIV * slot * 4 + (size_t)plan.W * NQT * 4 * RT * 4 + (size_t)plan.W * NST_PRIV * sizeof(uint64_t)
-        : (size_t)NSTAGE * slot * 4 + (size_t)plan.W * NQT * 4 * RT * 4 + 2 * NSTAGE * sizeof(uint64_t);
+        : (size_t)NSTAGE * slot * 4 + (size_t)plan.W * NQT * 4 * RT * 4 + 2 * NSTAGE * sizeof(uint64_t) + 16;
     if (smem > 227 * 1024) return fail(GPTPINN_E_UNSUPPORTED, "configuration needs %zu bytes of shared memory", smem);
     sweep_launch_fn fn = kLaunch[pde][n - 1];
     if (!fn) return fail(GPTPINN_E_UNSUPPORTED, "no kernel compiled for pde=%d n=%d", pde, n);

@@ -94,12 +94,14 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
     uint64_t *bars = reinterpret_cast<uint64_t *>(Tall + p.W * TT);
     uint64_t *full = PRIV ? bars + warp * NST : bars;
     uint64_t *empty = bars + NST;            // shared mode only
+    uint32_t *issued = reinterpret_cast<uint32_t *>(bars + (PRIV ? p.W * NST : 2 * NST));   // shared mode: tiles issued so far
 
     if (threadIdx.x == 0) {
         if (PRIV) {
             for (int s = 0; s < p.W * NST; ++s) mbar_init(&bars[s], 1);
         } else {
             for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], p.W); }
+            *issued = 0u;
         }
         mbar_fence_init();
     }
@@ -124,14 +126,23 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
         bulk_g2s(ring + s * SLOT, p.packed + (size_t)next_tile * SLOT, SLOT * 4, &full[s]);
         next_tile = (next_tile + 1 == tiles_pp) ? 0u : next_tile + 1;
     };
-    if (producer) {
-        if (PRIV) { for (uint32_t s = 0; s < (uint32_t)NST; ++s) issue_priv(s); }
-        else { for (uint32_t lt = 0; lt < (uint32_t)LOOKAHEAD && lt < total; ++lt) issue_shared(lt); }
-    }
+    if (PRIV && producer)
+        for (uint32_t s = 0; s < (uint32_t)NST; ++s) issue_priv(s);
 
     auto acquire = [&]() -> const float * {
         if (!PRIV) {
-            if (producer) { const uint32_t lt = gt + LOOKAHEAD; if (lt < total) issue_shared(lt); }
+            // shared ring: whichever warp reaches tile gt first makes sure tiles up to gt + LOOKAHEAD are in flight
+            // (a fixed producer warp loses the issue-priority race on its SMSP and starves the ring)
+            if (lane == 0) {
+                uint32_t want = gt + LOOKAHEAD;
+                if (want >= total) want = total - 1;
+                uint32_t cur = *reinterpret_cast<volatile uint32_t *>(issued);
+                while (cur <= want) {
+                    const uint32_t old = atomicCAS(issued, cur, cur + 1);
+                    if (old == cur) { issue_shared(cur); cur = cur + 1; }
+                    else cur = old;
+                }
+            }
             __syncwarp();
         }
         const uint32_t s = gt % NST;
