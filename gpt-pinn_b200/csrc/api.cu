@@ -131,8 +131,10 @@ static double item_instr(int pde, int n, int M, int SL, long long rows_total, lo
     const double rows_lane = (double)tiles * ((rt + RL - 1) / RL);     // every tile costs whole lane-rows
     // T: items with <= GP_REGT_MAX_SL sibling lanes form their T rows in registers (per row: extra loads + 2n FMA),
     // wider items build a per-warp T block in shared memory once per tile; plus ring bookkeeping per tile
-    const double build = SL <= GP_REGT_MAX_SL ? (double)tiles * 90.0 + rows_lane * (2.0 * n + 6.0)
-                                               : (double)tiles * (36.0 * (n / 4 + 1) * rt / 32.0 + 90.0);
+    // per-tile ring cost in instruction-equivalents (mbarrier wait + first-row load latency, measured on B200)
+    const double ring = rt == RT_SHARED ? 300.0 : 150.0;
+    const double build = SL <= GP_REGT_MAX_SL ? (double)tiles * ring + rows_lane * (2.0 * n + 6.0)
+                                               : (double)tiles * (36.0 * (n / 4 + 1) * rt / 32.0 + ring);
     (void)rows_total;
     // measured issue efficiency relative to M = 5 (KG n = 15 single-round runs: 0.595 / 0.526 / 0.453 / 0.304 of FP32 peak)
     const double rel = M >= 5 ? 1.0 : (M == 4 ? 0.895 : (M >= 2 ? 0.835 : 0.624));
