@@ -112,6 +112,89 @@ __global__ void __launch_bounds__(256, 1) k_bwd2(float *out, const float *in, in
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+
+// forward contraction with the two dot products packed in one FFMA2: (u[m], t[m]) += (P[k], T[k]) * (c[m][k], c[m][k])
+template <int M>
+__global__ void __launch_bounds__(256, 1) k_fwd_pt2(float *out, const float *in, int iters)
+{
+    unsigned long long cc[M][K], pt[K], acc[M];
+    for (int k = 0; k < K; ++k) pt[k] = pack2(in[k + threadIdx.x % 7], in[k + 1 + threadIdx.x % 5]);
+    for (int m = 0; m < M; ++m) { acc[m] = pack2(0.f, 0.f); for (int k = 0; k < K; ++k) { float v = in[64 + m * K + k]; cc[m][k] = pack2(v, v); } }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int m = 0; m < M; ++m) acc[m] = fma2(pt[k], cc[m][k], acc[m]);
+#pragma unroll
+        for (int k = 0; k < K; k += 4) pt[k] += 1;
+    }
+    float s = 0.f;
+    for (int m = 0; m < M; ++m) { float a, b; unpack2(acc[m], a, b); s += a + b; }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// whole row step of the proposed M = 4 kernel: packed forward (FFMA2) + plain gradient FFMAs reading the halves of the pairs
+template <int M>
+__global__ void __launch_bounds__(256, 1) k_row_pt2(float *out, const float *in, int iters)
+{
+    unsigned long long cc[M][K], pt[K];
+    float g[M][K];
+    for (int k = 0; k < K; ++k) pt[k] = pack2(in[k + threadIdx.x % 7], in[k + 1 + threadIdx.x % 5]);
+    for (int m = 0; m < M; ++m) for (int k = 0; k < K; ++k) { float v = in[64 + m * K + k]; cc[m][k] = pack2(v, v); g[m][k] = 0.f; }
+    for (int it = 0; it < iters; ++it) {
+        unsigned long long acc[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) acc[m] = pack2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int m = 0; m < M; ++m) acc[m] = fma2(pt[k], cc[m][k], acc[m]);
+        float first[M], w2[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) { float u, t; unpack2(acc[m], u, t); first[m] = fmaf(0.3f, u * u, t); w2[m] = first[m] * (0.6f * u); }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float pk, tk;
+            unpack2(pt[k], pk, tk);
+#pragma unroll
+            for (int m = 0; m < M; ++m) { g[m][k] = fmaf(first[m], tk, g[m][k]); g[m][k] = fmaf(w2[m], pk, g[m][k]); }
+        }
+#pragma unroll
+        for (int k = 0; k < K; k += 4) pt[k] += 1;
+    }
+    float s = 0.f;
+    for (int m = 0; m < M; ++m) for (int k = 0; k < K; ++k) s += g[m][k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// the same row step with plain FFMAs (what the shipped kernel does), for comparison
+template <int M>
+__global__ void __launch_bounds__(256, 1) k_row_plain(float *out, const float *in, int iters)
+{
+    float c[M][K], p[K], t[K], g[M][K];
+    for (int k = 0; k < K; ++k) { p[k] = in[k + threadIdx.x % 7]; t[k] = in[k + 1 + threadIdx.x % 5]; }
+    for (int m = 0; m < M; ++m) for (int k = 0; k < K; ++k) { c[m][k] = in[64 + m * K + k]; g[m][k] = 0.f; }
+    for (int it = 0; it < iters; ++it) {
+        float first[M], w2[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            float u = 0.f, tt = 0.f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) { u = fmaf(p[k], c[m][k], u); tt = fmaf(t[k], c[m][k], tt); }
+            first[m] = fmaf(0.3f, u * u, tt); w2[m] = first[m] * (0.6f * u);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int m = 0; m < M; ++m) { g[m][k] = fmaf(first[m], t[k], g[m][k]); g[m][k] = fmaf(w2[m], p[k], g[m][k]); }
+#pragma unroll
+        for (int k = 0; k < K; k += 4) { p[k] += 1e-9f; t[k] += 1e-9f; }
+    }
+    float s = 0.f;
+    for (int m = 0; m < M; ++m) for (int k = 0; k < K; ++k) s += g[m][k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename F>
 static void run(const char *name, F launch, double fma_per_thread_iter, int iters, int threads)
 {
@@ -144,7 +227,7 @@ int main()
     cudaMalloc(&in, 4096 * sizeof(float));
     cudaMemset(in, 0, 4096 * sizeof(float));
     const int iters = 20000;
-    for (int threads : {256, 512}) {
+    for (int threads : {256}) {
         run("bwd M=5", [&](int it) { k_bwd<5><<<148, threads>>>(out, in, it); }, 5 * K, iters, threads);
         run("bwd M=4", [&](int it) { k_bwd<4><<<148, threads>>>(out, in, it); }, 4 * K, iters, threads);
         run("fwd k-outer M=5", [&](int it) { k_fwd<5, true><<<148, threads>>>(out, in, it); }, 5 * K, iters, threads);
@@ -152,6 +235,10 @@ int main()
         run("fwd m-outer M=5", [&](int it) { k_fwd<5, false><<<148, threads>>>(out, in, it); }, 5 * K, iters, threads);
         run("fwd2 (f32x2) M=4", [&](int it) { k_fwd2<4><<<148, threads>>>(out, in, it); }, 4 * K, iters, threads);
         run("bwd2 (f32x2) M=4", [&](int it) { k_bwd2<4><<<148, threads>>>(out, in, it); }, 4 * K, iters, threads);
+        run("fwd (P,T)x(c,c) f32x2 M=4", [&](int it) { k_fwd_pt2<4><<<148, threads>>>(out, in, it); }, 2 * 4 * K, iters, threads);
+        run("row step f32x2 fwd M=4", [&](int it) { k_row_pt2<4><<<148, threads>>>(out, in, it); }, 4 * 4 * K, iters / 2, threads);
+        run("row step plain M=4", [&](int it) { k_row_plain<4><<<148, threads>>>(out, in, it); }, 4 * 4 * K, iters / 2, threads);
+        run("row step plain M=5", [&](int it) { k_row_plain<5><<<148, threads>>>(out, in, it); }, 4 * 5 * K, iters / 2, threads);
     }
     return 0;
 }
