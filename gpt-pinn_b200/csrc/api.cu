@@ -114,7 +114,7 @@ static inline uint64_t key_of(const ParamRow &r)
 }
 
 struct Plan {
-    int M = 1, SL = 1, W = 1, ctas = 1, rounds = 1, groups = 0, priv = 0;
+    int M = 1, SL = 1, W = 1, ctas = 1, rounds = 1, groups = 0, priv = 0, K = 1;
     std::vector<ItemDesc> items;
     std::vector<SibDesc> sibs;
 };
@@ -125,10 +125,13 @@ static double per_row_instr(int pde, int n, int M)
     const double fma = (pde == PDE_B ? 6.0 : 4.0) * n;
     return M * (fma + 8.0) + (pde == PDE_B ? 3.0 : 2.0) * ((n + 3) / 4) + 8.0;
 }
-static double item_instr(int pde, int n, int M, int SL, long long rows_total, long long tiles, int rt)
+static double item_instr(int pde, int n, int M, int SL, long long rows_total, long long tiles_pass, int rt, int K = 1)
 {
     const int RL = 32 / SL;
+    const long long tiles = (tiles_pass + K - 1) / K;                  // a team of K warps splits the tiles of a pass
     const double rows_lane = (double)tiles * ((rt + RL - 1) / RL);     // every tile costs whole lane-rows
+    // end-of-pass team sum: per parameter slot 2 named barriers + (n/4+1) stores and K*(n/4+1) loads + adds
+    const double team = K > 1 ? M * (140.0 + (n / 4 + 1) * (2.0 + 2.0 * K) + (n + 1.0) * (K - 1)) : 0.0;
     // T: items with <= GP_REGT_MAX_SL sibling lanes form their T rows in registers (per row: extra loads + 2n FMA),
     // wider items build a per-warp T block in shared memory once per tile; plus ring bookkeeping per tile
     // per-tile ring cost in instruction-equivalents (mbarrier wait + first-row load latency, measured on B200)
@@ -138,7 +141,7 @@ static double item_instr(int pde, int n, int M, int SL, long long rows_total, lo
     (void)rows_total;
     // measured issue efficiency relative to M = 5 (KG n = 15 single-round runs: 0.595 / 0.526 / 0.453 / 0.304 of FP32 peak)
     const double rel = M >= 5 ? 1.0 : (M == 4 ? 0.895 : (M >= 2 ? 0.835 : 0.624));
-    return (rows_lane * per_row_instr(pde, n, M) + build) / rel;
+    return (rows_lane * per_row_instr(pde, n, M) + build + team) / rel;
 }
 // measured issue efficiency of one SMSP vs resident warps (B200, KG n=15: 1 warp 0.49/0.60, 2 warps 1.0 relative)
 static double smsp_eff(double warps_per_smsp)
@@ -206,12 +209,12 @@ static void decompose(const std::vector<int> &gstart, int M, int sl_cap, std::ve
 // do not fill a whole "round" of `workers` warps would leave most warps idle for a full item time,
 // so that tail is cut into 2^k-times smaller items (k chosen by the cost model): the last warps
 // to finish then differ by one *small* item.
-static void refine_tail(std::vector<Chunk> &ch, int M, int workers, int pde, int n, long long tiles, int rt)
+static void refine_tail(std::vector<Chunk> &ch, int M, int workers, int pde, int n, long long tiles, int rt, int K = 1)
 {
     if (ch.empty()) return;
     auto cost_of = [&](const std::vector<Chunk> &v) {
         std::vector<double> t(v.size());
-        for (size_t i = 0; i < v.size(); ++i) t[i] = item_instr(pde, n, M, v[i].SL, 0, tiles, rt);
+        for (size_t i = 0; i < v.size(); ++i) t[i] = item_instr(pde, n, M, v[i].SL, 0, tiles, rt, K);
         return makespan(t, workers);
     };
     const size_t full = (ch.size() / (size_t)workers) * (size_t)workers;     // items in whole rounds keep their size
@@ -264,8 +267,10 @@ static int make_plan(std::vector<ParamRow> &rows, int pde, int n, int n_sm, cons
         return fail(GPTPINN_E_INVALID, "cfg_SL must be 0 or a power of two <= 32");
     if (mode < 0 || mode > 2) return fail(GPTPINN_E_INVALID, "cfg_mode must be 0, 1 or 2");
 
+    if (a->cfg_K != 0 && !(a->cfg_K == 1 || a->cfg_K == 2 || a->cfg_K == 4 || a->cfg_K == 8))
+        return fail(GPTPINN_E_INVALID, "cfg_K must be 0, 1, 2, 4 or 8");
     double best = 1e300;
-    int bM = 0, bSL = 0, bW = 0, bPriv = 0;
+    int bM = 0, bSL = 0, bW = 0, bPriv = 0, bK = 1;
     std::vector<Chunk> bestChunks, ch;
     int maxS = 1;
     for (int g = 0; g < plan.groups; ++g) maxS = std::max(maxS, gstart[g + 1] - gstart[g]);
@@ -278,8 +283,13 @@ static int make_plan(std::vector<ParamRow> &rows, int pde, int n, int n_sm, cons
         const int maxw = maxw_for_m(M);
         // ---- private rings: dynamic tickets, mixed item sizes ----
         if (mode != 1) {
-            const int wsmem = (int)((227.0 * 1024 - 64) / (NST_PRIV * slot_p + (n / 4 + 1) * 4 * RT_PRIV * 4 + NST_PRIV * 8));
-            const int maxwp = std::max(1, std::min(maxw, wsmem));
+            const int wsmem = (int)((227.0 * 1024 - 96) / (NST_PRIV * slot_p + tblock_floats(pde, n, M, RT_PRIV) * 4 + NST_PRIV * 8 + TEAM_BYTES_PER_WARP));
+            const int maxw1 = std::max(1, std::min(maxw, wsmem));
+          for (int K = 1; K <= 8; K <<= 1) {
+            // teams of K warps share an item (finer time quanta for grids that give each warp only a few items)
+            if (a->cfg_K > 0 && K != a->cfg_K) continue;
+            if (K > maxw1 || K > tiles_p) continue;
+            const int maxwp = (maxw1 / K) * K;
             for (int cap = 32; cap >= 1; cap >>= 1) {
                 std::vector<Chunk> base;
                 if (a->cfg_SL > 0) {
@@ -290,24 +300,26 @@ static int make_plan(std::vector<ParamRow> &rows, int pde, int n, int n_sm, cons
                 } else {
                     decompose(gstart, M, cap, base);
                     if (cap < 32 && !base.empty() && base.front().SL < cap) continue;  // the cap does not bind: same as the previous one
-                    if ((long long)base.size() > 12LL * n_sm * maxwp) break;           // finer than 12 items per resident warp never pays
+                    if ((long long)base.size() * K > 12LL * n_sm * maxwp) break;       // finer than 12 items per resident team never pays
                 }
                 // with at least one item per resident warp the full warp count is always best
-                const int wlo = (a->cfg_W == 0 && (long long)base.size() >= (long long)n_sm * maxwp) ? maxwp : std::max(1, maxwp - 3);
-                for (int W = maxwp; W >= wlo; --W) {
-                    if (a->cfg_W > 0 && W != std::min(a->cfg_W, maxwp)) continue;
+                const int wlo = (a->cfg_W == 0 && (long long)base.size() * K >= (long long)n_sm * maxwp) ? maxwp : std::max(K, maxwp - 3);
+                for (int W = maxwp; W >= wlo; W -= K) {
+                    if (a->cfg_W > 0 && W != std::max(K, std::min(a->cfg_W, maxwp) / K * K)) continue;
+                    const int TPC = W / K;                                  // teams per CTA
                     ch = base;
-                    if (a->cfg_SL == 0) refine_tail(ch, M, n_sm * W, pde, n, tiles_p, RT_PRIV);
+                    if (a->cfg_SL == 0) refine_tail(ch, M, n_sm * TPC, pde, n, tiles_p, RT_PRIV, K);
                     std::vector<double> t(ch.size());
-                    for (size_t i = 0; i < ch.size(); ++i) t[i] = item_instr(pde, n, M, ch[i].SL, 0, tiles_p, RT_PRIV);
-                    const int Wuse = (int)std::max<long long>(1, std::min<long long>(W, ((long long)ch.size() + n_sm - 1) / n_sm));
-                    const double wps = Wuse / 4.0;
-                    const double issue = makespan(t, n_sm * Wuse) * std::max(1.0, std::ceil(wps)) / smsp_eff(std::max(1.0, wps));
+                    for (size_t i = 0; i < ch.size(); ++i) t[i] = item_instr(pde, n, M, ch[i].SL, 0, tiles_p, RT_PRIV, K);
+                    const int Tuse = (int)std::max<long long>(1, std::min<long long>(TPC, ((long long)ch.size() + n_sm - 1) / n_sm));
+                    const double wps = Tuse * K / 4.0;
+                    const double issue = makespan(t, n_sm * Tuse) * std::max(1.0, std::ceil(wps)) / smsp_eff(std::max(1.0, wps));
                     const double l2 = (double)ch.size() * tiles_p * slot_p / kL2BytesPerCycle;
-                    const double cst = std::max(issue, l2);
-                    if (cst < best) { best = cst; bM = M; bSL = ch.empty() ? 1 : ch.front().SL; bW = Wuse; bPriv = 1; bestChunks = ch; }
+                    const double cst = std::max(issue, l2) * (1.0 + 0.005 * (K > 1));      // ties go to independent warps
+                    if (cst < best) { best = cst; bM = M; bSL = ch.empty() ? 1 : ch.front().SL; bW = Tuse * K; bPriv = 1; bK = K; bestChunks = ch; }
                 }
             }
+          }
         }
         // ---- shared ring: static rounds, uniform item size ----
         if (mode != 2) {
@@ -328,13 +340,13 @@ static int make_plan(std::vector<ParamRow> &rows, int pde, int n, int n_sm, cons
                     }
                     const double l2 = rounds * ctas * tiles_s * slot_s / kL2BytesPerCycle;
                     const double cst = std::max(issue, l2) * 1.02;          // ties go to the private rings
-                    if (cst < best) { best = cst; bM = M; bSL = SL; bW = W; bPriv = 0; }
+                    if (cst < best) { best = cst; bM = M; bSL = SL; bW = W; bPriv = 0; bK = 1; }
                 }
             }
         }
     }
     if (bM == 0) return fail(GPTPINN_E_INVALID, "no feasible sweep configuration");
-    plan.M = bM; plan.SL = bSL; plan.W = std::max(1, bW); plan.priv = bPriv;
+    plan.M = bM; plan.SL = bSL; plan.W = std::max(1, bW); plan.priv = bPriv; plan.K = bK;
     if (!bPriv) {
         bestChunks.clear();
         for (int g = 0; g < plan.groups; ++g)
@@ -361,8 +373,9 @@ static int make_plan(std::vector<ParamRow> &rows, int pde, int n, int n_sm, cons
     }
     const long long nit = (long long)plan.items.size();
     if (bPriv) {
-        plan.ctas = (int)std::min<long long>(n_sm, (nit + plan.W - 1) / plan.W);
-        plan.rounds = (int)((nit + (long long)plan.ctas * plan.W - 1) / ((long long)plan.ctas * plan.W));
+        const int tpc = plan.W / plan.K;
+        plan.ctas = (int)std::min<long long>(n_sm, (nit + tpc - 1) / tpc);
+        plan.rounds = (int)((nit + (long long)plan.ctas * tpc - 1) / ((long long)plan.ctas * tpc));
     } else {
         plan.ctas = (int)std::min<long long>(n_sm, (nit + plan.W - 1) / plan.W);
         plan.rounds = (int)((nit + (long long)plan.ctas * plan.W - 1) / ((long long)plan.ctas * plan.W));
@@ -449,18 +462,20 @@ static int run_sweep(gptpinn_handle *h, int pde, int n, const Segments &seg, Pac
     p.W = plan.W;
     p.rounds = plan.rounds;
     p.counter = h->counter;
+    p.K = plan.priv ? plan.K : 1;
 
-    const int NQT = n / 4 + 1;
+    const size_t tblk = (size_t)tblock_floats(pde, n, plan.M, RT) * 4;
     const size_t smem = plan.priv
-        ? (size_t)plan.W * NST_PRIV * slot * 4 + (size_t)plan.W * NQT * 4 * RT * 4 + (size_t)plan.W * NST_PRIV * sizeof(uint64_t)
-        : (size_t)NSTAGE * slot * 4 + (size_t)plan.W * NQT * 4 * RT * 4 + 2 * NSTAGE * sizeof(uint64_t) + 16;
+        ? (size_t)plan.W * NST_PRIV * slot * 4 + (size_t)plan.W * tblk + (((size_t)plan.W * NST_PRIV * sizeof(uint64_t) + 15) & ~(size_t)15)
+              + (size_t)plan.W * TEAM_BYTES_PER_WARP
+        : (size_t)NSTAGE * slot * 4 + (size_t)plan.W * tblk + 2 * NSTAGE * sizeof(uint64_t) + 16;
     if (smem > 227 * 1024) return fail(GPTPINN_E_UNSUPPORTED, "configuration needs %zu bytes of shared memory", smem);
     sweep_launch_fn fn = kLaunch[pde][n - 1];
     if (!fn) return fail(GPTPINN_E_UNSUPPORTED, "no kernel compiled for pde=%d n=%d", pde, n);
     if (p.n_items > 0) CUDA_TRY(fn(p, plan.M, plan.priv, plan.ctas, smem, st));
     if (info) {
         info->M = plan.M; info->SL = plan.SL; info->W = plan.W; info->items = p.n_items; info->groups = plan.groups;
-        info->ctas = plan.ctas; info->rounds = plan.rounds; info->priv = plan.priv; info->kernels_launched = p.n_items > 0 ? 2 : 1;
+        info->ctas = plan.ctas; info->rounds = plan.rounds; info->priv = plan.priv; info->K = plan.priv ? plan.K : 1; info->kernels_launched = p.n_items > 0 ? 2 : 1;
         info->smem_bytes = (int)smem; info->tiles_per_pass = (int)tiles;
     }
     return GPTPINN_OK;
@@ -619,7 +634,7 @@ extern "C" int gptpinn_kg_plan(const double *grid_host, int Np, int n, int NR, i
         return fail(GPTPINN_E_INVALID, "gptpinn_kg_plan: bad arguments");
     gptpinn_sweep_args a;
     memset(&a, 0, sizeof(a));
-    if (cfg) { a.cfg_M = cfg->cfg_M; a.cfg_SL = cfg->cfg_SL; a.cfg_W = cfg->cfg_W; a.cfg_mode = cfg->cfg_mode; }
+    if (cfg) { a.cfg_M = cfg->cfg_M; a.cfg_SL = cfg->cfg_SL; a.cfg_W = cfg->cfg_W; a.cfg_mode = cfg->cfg_mode; a.cfg_K = cfg->cfg_K; }
     std::vector<ParamRow> rows((size_t)Np);
     for (int i = 0; i < Np; ++i) {
         rows[i].tp0 = (float)grid_host[3 * i]; rows[i].tp1 = (float)grid_host[3 * i + 1];
@@ -631,7 +646,7 @@ extern "C" int gptpinn_kg_plan(const double *grid_host, int Np, int n, int NR, i
     if (rc) return rc;
     memset(info, 0, sizeof(*info));
     info->M = plan.M; info->SL = plan.SL; info->W = plan.W; info->items = (int)plan.items.size(); info->groups = plan.groups;
-    info->ctas = plan.ctas; info->rounds = plan.rounds; info->priv = plan.priv;
+    info->ctas = plan.ctas; info->rounds = plan.rounds; info->priv = plan.priv; info->K = plan.priv ? plan.K : 1;
     for (int i = 0; i < 6; ++i) sl_hist[i] = 0;
     std::vector<char> seen((size_t)Np, 0);
     int cov = 0;

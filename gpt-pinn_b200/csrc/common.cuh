@@ -31,8 +31,21 @@ constexpr int NSTAGE   = 4;                  // shared ring depth
 constexpr int LOOKAHEAD = 2;                 // shared ring: tiles in flight ahead of the consumers
 constexpr int NST_PRIV = 3;                  // private ring depth (per warp)
 constexpr int MAX_SEG  = 4;
+constexpr int RED_STRIDE = 20;               // floats per lane in the team-reduction buffer (16 used; 80-B stride: conflict-free LDS.128)
+constexpr int TEAM_BYTES_PER_WARP = 32 * RED_STRIDE * 4 + 4;     // reduction rows + the team's ticket slot
 
 constexpr int PDE_KG = 0, PDE_B = 1, PDE_AC = 2;
+
+#ifndef GP_PACKED_FWD
+#define GP_PACKED_FWD 0
+#endif
+// Experimental (off): kernels with M == 4 parameters per thread (Klein-Gordon, Allen-Cahn) run a packed FFMA2 forward
+// contraction; their per-warp T block holds interleaved (P, T) pairs and is twice the plain size.  Measured on B200
+// it is 8 % SLOWER than the scalar M = 4 kernel (three 64-bit operands always collide in the register file, and the
+// scalar backward FFMAs lose their operand reuse), so it stays disabled; see DESIGN.md "what did not work".
+// Host (shared-memory sizing) and device agree through these two functions.
+__host__ __device__ constexpr bool use_packed_fwd(int pde, int M) { return GP_PACKED_FWD && pde != PDE_B && M == 4; }
+__host__ __device__ constexpr int tblock_floats(int pde, int n, int M, int rt) { return (use_packed_fwd(pde, M) ? 2 : 1) * (n / 4 + 1) * 4 * rt; }
 
 template <int PDE> struct PdeTraits;
 template <> struct PdeTraits<PDE_KG> {      // residual: Ptt,Pxx,P | xcos,fhat ; IC: PIC,PICt | u1,u2 ; BC: PBC | BCu
@@ -77,6 +90,8 @@ struct SweepParams {
     int            W;                // warps per CTA
     int            rounds;           // shared-ring kernels: static rounds of gridDim.x * W items
     unsigned int  *counter;          // private-ring kernels: global work-item ticket (zeroed before launch)
+    int            K;                // private-ring kernels: warps per team (power of two dividing W); a team shares one
+                                     // work item, its warps take every K-th tile and sum their gradients once per epoch
 };
 
 __device__ __forceinline__ void fence_proxy_async()

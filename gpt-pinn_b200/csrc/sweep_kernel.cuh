@@ -46,6 +46,11 @@ __device__ __forceinline__ void load_quad(const float *blk, int r, int q, float 
     const float4 x = ld4(blk + q * (4 * RT) + r * 4);
     v[4 * q + 0] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
 }
+__device__ __forceinline__ void load_quad_lin(const float *row, int q, float *v)
+{
+    const float4 x = ld4(row + 4 * q);
+    v[4 * q + 0] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+}
 template <int NQX, int RT>
 __device__ __forceinline__ void load_row(const float *blk, int r, float (&v)[4 * NQX])
 {
@@ -53,12 +58,31 @@ __device__ __forceinline__ void load_row(const float *blk, int r, float (&v)[4 *
     for (int q = 0; q < NQX; ++q) load_quad<RT>(blk, r, q, v);
 }
 
-template <int N>
-__device__ __forceinline__ float dotn(const float *a, const float (&c)[N], float init)
+// Coefficient registers.  Plain kernels hold c as floats; the packed-forward kernels (use_packed_fwd) hold every c[k]
+// as the 64-bit pair (c[k], c[k]) so that one FFMA2 (fma.rn.f32x2) advances the P and the T contraction of a row
+// together: (u, t) += (P[k], T[k]) * (c[k], c[k]).  An FFMA2 reads three 64-bit register pairs in one dispatch slot,
+// where the two scalar FFMAs it replaces each pay a second register-file cycle for their third operand.
+template <bool PK> struct Coef { typedef float type; };
+template <> struct Coef<true> { typedef unsigned long long type; };
+__device__ __forceinline__ float cget(float v) { return v; }
+__device__ __forceinline__ float cget(unsigned long long v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ void cset(float &d, float v) { d = v; }
+__device__ __forceinline__ void cset(unsigned long long &d, float v) { asm("mov.b64 %0, {%1, %1};" : "=l"(d) : "f"(v)); }
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ float lo32(unsigned long long v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float hi32(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
+
+template <int N, typename CT>
+__device__ __forceinline__ float dotn(const float *a, const CT (&c)[N], float init)
 {
     float s = init;
 #pragma unroll
-    for (int k = 0; k < N; ++k) s = fmaf(a[k], c[k], s);
+    for (int k = 0; k < N; ++k) s = fmaf(a[k], cget(c[k]), s);
     return s;
 }
 
@@ -77,7 +101,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
     constexpr int NQ = (N + 3) / 4;          // column quads of a P block that hold data
     constexpr int NQT = N / 4 + 1;           // quads of T: N columns + the forcing column
     constexpr int SLOT = SlotFloats<PDE, RT>::value;
-    constexpr int TT = NQT * QS;
+    constexpr bool PK = use_packed_fwd(PDE, M);   // T block holds interleaved (P[k], T[k]) pairs, c is held as (c, c)
+    constexpr int TT = (PK ? 2 : 1) * NQT * QS;
+    typedef typename Coef<PK>::type creg;
     constexpr int VEC0 = TR::NARR * ARR, VEC1 = VEC0 + RT;
     constexpr int NST = PRIV ? NST_PRIV : NSTAGE;
     constexpr unsigned FULLM = 0xffffffffu;
@@ -95,6 +121,15 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
     uint64_t *full = PRIV ? bars + warp * NST : bars;
     uint64_t *empty = bars + NST;            // shared mode only
     uint32_t *issued = reinterpret_cast<uint32_t *>(bars + (PRIV ? p.W * NST : 2 * NST));   // shared mode: tiles issued so far
+    // PRIV teams: K consecutive warps share one work item.  Warp tw of a team takes the tiles with index = tw (mod K)
+    // of every pass, so the team reads the stream once per pass, and the K partial gradients are summed through
+    // shared memory at the end of the pass (fixed order: every warp of the team ends up with the same bits).
+    const int K = PRIV ? p.K : 1;
+    const int team = warp / K, tw = warp & (K - 1);
+    float *red0 = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(bars) + ((p.W * NST * 8 + 15) & ~15));
+    float *redbuf = red0 + (size_t)team * K * 32 * RED_STRIDE;                   // this team's [K][32][RED_STRIDE] rows
+    int *team_item = reinterpret_cast<int *>(red0 + (size_t)p.W * 32 * RED_STRIDE);
+    auto team_bar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(K * 32) : "memory"); };
 
     if (threadIdx.x == 0) {
         if (PRIV) {
@@ -113,7 +148,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
     const uint32_t total = PRIV ? 0u : (uint32_t)p.rounds * (uint32_t)(p.epochs + 1) * tiles_pp;
     const bool producer = PRIV ? (lane == 0) : (threadIdx.x == 0);
     // ---- private ring state ----
-    uint32_t next_tile = 0;                  // stream position of the next tile to issue (lane 0)
+    uint32_t next_tile = (uint32_t)tw;       // stream position of the next tile to issue (lane 0); K <= tiles_pp
 
     auto issue_shared = [&](uint32_t lt) {
         const uint32_t s = lt % NST, use = lt / NST;
@@ -124,7 +159,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
     auto issue_priv = [&](uint32_t s) {
         mbar_arrive_expect_tx(&full[s], SLOT * 4);
         bulk_g2s(ring + s * SLOT, p.packed + (size_t)next_tile * SLOT, SLOT * 4, &full[s]);
-        next_tile = (next_tile + 1 == tiles_pp) ? 0u : next_tile + 1;
+        next_tile += (uint32_t)K;
+        if (next_tile >= tiles_pp) next_tile = (uint32_t)tw;
     };
     if (PRIV && producer)
         for (uint32_t s = 0; s < (uint32_t)NST; ++s) issue_priv(s);
@@ -165,9 +201,16 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
     for (int round = 0;; ++round) {
         int item;
         if (PRIV) {
-            int tk = 0;
-            if (lane == 0) tk = (int)atomicAdd(p.counter, 1u);
-            item = __shfl_sync(FULLM, tk, 0);
+            if (K == 1) {
+                int tk = 0;
+                if (lane == 0) tk = (int)atomicAdd(p.counter, 1u);
+                item = __shfl_sync(FULLM, tk, 0);
+            } else {
+                // the slot is rewritten only after the >= 2M team barriers of a pass, so one barrier orders write -> read
+                if (tw == 0 && lane == 0) team_item[team] = (int)atomicAdd(p.counter, 1u);
+                team_bar();
+                item = team_item[team];
+            }
             if (item >= p.n_items) break;
         } else {
             if (round >= p.rounds) break;
@@ -180,7 +223,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
         const int SL = it.SL, RL = 32 / SL;
         const int sl = lane & (SL - 1), slice = lane / SL;
 
-        float c[M][N], g[M][N];
+        creg c[M][N];
+        float g[M][N];
         float sp0[M], sp1[M], mn[M];
 #pragma unroll
         for (int m = 0; m < M; ++m) {
@@ -194,7 +238,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
             }
 #pragma unroll
             for (int k = 0; k < N; ++k)
-                c[m][k] = valid ? (p.c0_per_param ? p.c0[(size_t)oi * N + k] : p.c0[k]) : 0.f;
+                cset(c[m][k], valid ? (p.c0_per_param ? p.c0[(size_t)oi * N + k] : p.c0[k]) : 0.f);
             mn[m] = __int_as_float(0x7f800000);
         }
 
@@ -210,7 +254,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
             }
 
             // ------------------------------ segment 0: PDE residual rows ------------------
-            for (int t = 0; t < p.ntile[0]; ++t) {
+            int gbase = 0;                          // pass-relative index of the segment's first tile
+            for (int t = (tw - gbase) & (K - 1); t < p.ntile[0]; t += K) {
                 const float *slot = acquire();
                 if (active && SL <= REGT_MAX_SL) {
                     // ---- few sibling lanes: a T row is used by at most REGT_MAX_SL lanes, so staging the whole T block
@@ -311,18 +356,71 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                             }
                             set_comp(tv, N % 4, fc);
                         }
-                        st4(Tw + o, tv);
+                        if constexpr (PK) {      // interleave with the P quad: pair-quads 2q, 2q+1 = (P0,T0,P1,T1), (P2,T2,P3,T3)
+                            float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (q < NQ) pv = ld4(slot + 2 * ARR + o);
+                            if (q == N / 4) set_comp(pv, N % 4, 0.f);        // the forcing pair is (0, forcing): it seeds (u, t)
+                            st4(Tw + (2 * q) * QS + r * 4, make_float4(pv.x, tv.x, pv.y, tv.y));
+                            st4(Tw + (2 * q + 1) * QS + r * 4, make_float4(pv.z, tv.z, pv.w, tv.w));
+                        } else {
+                            st4(Tw + o, tv);
+                        }
                     }
                     __syncwarp();
 
                     const float *Pblk = slot + (PDE == PDE_B ? 3 : 2) * ARR;
                     const int fhoff = (PDE == PDE_KG) ? VEC1 : VEC0;
                     int r = slice;
+                    float fh = 0.f;
+                    if (has_fhat) fh = slot[fhoff + r];
+                    if constexpr (PK) {
+                        unsigned long long PT[4 * NQT];         // pair k = (P[k], T[k]); pair N = (0, forcing)
+                        auto load_pairs = [&](int rr, int q2) {
+                            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(Tw + q2 * QS + rr * 4);
+                            PT[2 * q2] = v.x; PT[2 * q2 + 1] = v.y;
+                        };
+#pragma unroll
+                        for (int q2 = 0; q2 < 2 * NQT; ++q2) load_pairs(r, q2);
+                        for (; r < RT; r += RL) {
+                            const int rn = min(r + RL, RT - 1);
+                            float first[M], w2[M];
+                            unsigned long long acc[M];
+#pragma unroll
+                            for (int m = 0; m < M; ++m) acc[m] = PT[N];
+#pragma unroll
+                            for (int k = 0; k < N; ++k)
+#pragma unroll
+                                for (int m = 0; m < M; ++m) acc[m] = fma2(PT[k], c[m][k], acc[m]);
+#pragma unroll
+                            for (int m = 0; m < M; ++m) {
+                                const float u = lo32(acc[m]), tl = hi32(acc[m]);
+                                float d, nl;
+                                if constexpr (PDE == PDE_KG) { d = fmaf(sp0[m], u * u, tl); nl = sp1[m] * u; }
+                                else { const float u2 = u * u; d = fmaf(sp0[m], u2 * u, tl); nl = sp1[m] * u2; }
+                                lacc[m] = fmaf(d, d, lacc[m]);
+                                first[m] = has_fhat ? d + fh : d;
+                                w2[m] = first[m] * nl;
+                            }
+                            if (has_fhat) fh = slot[fhoff + rn];
+#pragma unroll
+                            for (int q = 0; q < NQT; ++q) {
+#pragma unroll
+                                for (int m = 0; m < M; ++m)
+#pragma unroll
+                                    for (int kk = 0; kk < 4; ++kk) {
+                                        const int k = 4 * q + kk;
+                                        if (k < N) {
+                                            g[m][k] = fmaf(first[m], hi32(PT[k]), g[m][k]);
+                                            g[m][k] = fmaf(w2[m], lo32(PT[k]), g[m][k]);
+                                        }
+                                    }
+                                load_pairs(rn, 2 * q); load_pairs(rn, 2 * q + 1);
+                            }
+                        }
+                    } else {
                     float Tv[4 * NQT], Pv[4 * NQ];
                     load_row<NQT, RT>(Tw, r, Tv);
                     load_row<NQ, RT>(Pblk, r, Pv);
-                    float fh = 0.f;
-                    if (has_fhat) fh = slot[fhoff + r];
                     if constexpr (PDE == PDE_B) {
                         const float *Xblk = slot + 2 * ARR;
                         float Xv[4 * NQ];
@@ -401,6 +499,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                             }
                         }
                     }
+                    }   // !PK
                 }
                 release();
             }
@@ -412,7 +511,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
             }
 
             // ------------------------------ segment 1: initial-condition rows -------------
-            for (int t = 0; t < p.ntile[1]; ++t) {
+            gbase += p.ntile[0];
+            for (int t = (tw - gbase) & (K - 1); t < p.ntile[1]; t += K) {
                 const float *slot = acquire();
                 if (active) {
                     for (int r = slice; r < RT; r += RL) {
@@ -457,7 +557,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
 
             // ------------------------------ segment 2 (3): boundary rows ------------------
             for (int seg = 2; seg < TR::NSEG; ++seg) {
-                for (int t = 0; t < p.ntile[seg]; ++t) {
+                gbase += p.ntile[seg - 1];
+                for (int t = (tw - gbase) & (K - 1); t < p.ntile[seg]; t += K) {
                     const float *slot = acquire();
                     if (active) {
                         for (int r = slice; r < RT; r += RL) {
@@ -506,12 +607,44 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                     for (int k = 0; k < N; ++k) g[m][k] += __shfl_xor_sync(FULLM, g[m][k], off);
                 }
             }
+            if (K > 1) {
+                // team sum, one parameter slot at a time: [K][32 lanes][g[0..N-1], loss]
+                float *mine = redbuf + (tw * 32 + lane) * RED_STRIDE;
+                const float *col = redbuf + lane * RED_STRIDE;
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+#pragma unroll
+                    for (int q = 0; q < NQT; ++q) {
+                        float4 v;
+                        v.x = (4 * q + 0 < N) ? g[m][4 * q + 0 < N ? 4 * q + 0 : 0] : lsum[m];
+                        v.y = (4 * q + 1 < N) ? g[m][4 * q + 1 < N ? 4 * q + 1 : 0] : lsum[m];
+                        v.z = (4 * q + 2 < N) ? g[m][4 * q + 2 < N ? 4 * q + 2 : 0] : lsum[m];
+                        v.w = (4 * q + 3 < N) ? g[m][4 * q + 3 < N ? 4 * q + 3 : 0] : lsum[m];
+                        st4(mine + 4 * q, v);
+                    }
+                    team_bar();
+                    float tot[4 * NQT];
+#pragma unroll
+                    for (int q = 0; q < NQT; ++q) load_quad_lin(col, q, tot);
+                    for (int k2 = 1; k2 < K; ++k2) {
+                        float oth[4 * NQT];
+#pragma unroll
+                        for (int q = 0; q < NQT; ++q) load_quad_lin(col + k2 * 32 * RED_STRIDE, q, oth);
+#pragma unroll
+                        for (int k = 0; k <= N; ++k) tot[k] += oth[k];
+                    }
+#pragma unroll
+                    for (int k = 0; k < N; ++k) g[m][k] = tot[k];
+                    lsum[m] = tot[N];
+                    team_bar();
+                }
+            }
             const bool rec = p.trace != nullptr && p.rec_every > 0 && (j % p.rec_every) == 0;
             const bool last = (j == p.epochs);
 #pragma unroll
             for (int m = 0; m < M; ++m) {
                 const float loss = lsum[m];       // = mean_R + mean_IC(s) + mean_BC(s)   (KG_models.py:45-50, B_models.py:42-46, AC_models.py:49-54)
-                if ((rec || last) && slice == 0 && (sl * M + m) < it.sib_count) {
+                if ((rec || last) && slice == 0 && tw == 0 && (sl * M + m) < it.sib_count) {
                     const int oi = p.sibs[it.sib_start + sl * M + m].out_idx;
                     if (rec) p.trace[(size_t)oi * p.nrec + j / p.rec_every] = loss;
                     if (last) {
@@ -519,14 +652,14 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                         p.m_out[oi] = mn[m];
                         if (p.c_out != nullptr) {
 #pragma unroll
-                            for (int k = 0; k < N; ++k) p.c_out[(size_t)oi * N + k] = c[m][k];
+                            for (int k = 0; k < N; ++k) p.c_out[(size_t)oi * N + k] = cget(c[m][k]);
                         }
                     }
                 }
                 if (!last) {
                     if (loss < mn[m]) mn[m] = loss;
 #pragma unroll
-                    for (int k = 0; k < N; ++k) c[m][k] = __fsub_rn(c[m][k], __fmul_rn(p.lr, g[m][k]));
+                    for (int k = 0; k < N; ++k) cset(c[m][k], __fsub_rn(cget(c[m][k]), __fmul_rn(p.lr, g[m][k])));
                 }
             }
         }   // epochs

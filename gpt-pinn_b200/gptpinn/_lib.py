@@ -42,13 +42,14 @@ class SweepArgs(C.Structure):
                 ("epochs", C.c_int), ("lr", C.c_double), ("rec_every", C.c_int),
                 ("c_out_dev", C.c_void_p), ("f_out_dev", C.c_void_p), ("m_out_dev", C.c_void_p),
                 ("trace_dev", C.c_void_p),
-                ("cfg_M", C.c_int), ("cfg_SL", C.c_int), ("cfg_W", C.c_int), ("cfg_mode", C.c_int)]
+                ("cfg_M", C.c_int), ("cfg_SL", C.c_int), ("cfg_W", C.c_int), ("cfg_mode", C.c_int),
+                ("cfg_K", C.c_int)]
 
 
 class SweepInfo(C.Structure):
     _fields_ = [("M", C.c_int), ("SL", C.c_int), ("W", C.c_int), ("items", C.c_int), ("groups", C.c_int),
                 ("ctas", C.c_int), ("rounds", C.c_int), ("kernels_launched", C.c_int),
-                ("smem_bytes", C.c_int), ("tiles_per_pass", C.c_int), ("priv", C.c_int)]
+                ("smem_bytes", C.c_int), ("tiles_per_pass", C.c_int), ("priv", C.c_int), ("K", C.c_int)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -145,7 +146,7 @@ def kg_plan(grid, n, NR=10000, NI=512, NB=1024, n_sm=148, cfg=None):
     grid = np.ascontiguousarray(np.asarray(grid, dtype=np.float64).reshape(-1, 3))
     a = SweepArgs()
     if cfg:
-        a.cfg_M, a.cfg_SL, a.cfg_W, a.cfg_mode = (int(cfg.get(k, 0)) for k in ("M", "SL", "W", "mode"))
+        a.cfg_M, a.cfg_SL, a.cfg_W, a.cfg_mode, a.cfg_K = (int(cfg.get(k, 0)) for k in ("M", "SL", "W", "mode", "K"))
     info = SweepInfo()
     hist = (C.c_int * 6)()
     cov = C.c_int(0)

@@ -98,6 +98,7 @@ def _run(fn_name, prob, keep, grid, gcols, n, c0, epochs, lr, rec_every, want_c,
     if cfg:
         args.cfg_M, args.cfg_SL, args.cfg_W = (int(cfg.get("M", 0)), int(cfg.get("SL", 0)), int(cfg.get("W", 0)))
         args.cfg_mode = int(cfg.get("mode", 0))
+        args.cfg_K = int(cfg.get("K", 0))
     info = SweepInfo()
     with torch.cuda.device(device):
         h = _lib.handle(device.index if device.index is not None else torch.cuda.current_device())

@@ -111,6 +111,8 @@ typedef struct {
      * per warp (SL, power of two <= 32), warps per CTA (W).                                   */
     int           cfg_M, cfg_SL, cfg_W;
     int           cfg_mode;    /* 0 = auto, 1 = shared-ring kernel, 2 = private-ring kernel      */
+    int           cfg_K;       /* 0 = auto; private-ring kernel: warps that team up on one work item
+                                * (1, 2, 4 or 8): they split the tiles of a pass and sum their gradients   */
 } gptpinn_sweep_args;
 
 /* filled by the sweep calls when non-NULL: what was launched (for bench.py / tests)           */
@@ -123,6 +125,7 @@ typedef struct {
     int   smem_bytes;
     int   tiles_per_pass;
     int   priv;                /* 1 = private-ring kernel (dynamic tickets), 0 = shared ring    */
+    int   K;                   /* warps per team (private-ring kernel), else 1                  */
 } gptpinn_sweep_info;
 
 int  gptpinn_version(void);

@@ -36,7 +36,8 @@ def _ac_run(d, n, grid, c0, epochs, lr, rec_every=0, cfg=None):
     return r
 
 
-@pytest.mark.parametrize("cfg", [None, dict(mode=1), dict(mode=2), dict(M=2, SL=1, mode=1), dict(M=1, SL=4, mode=2)])
+@pytest.mark.parametrize("cfg", [None, dict(mode=1), dict(mode=2), dict(M=2, SL=1, mode=1), dict(M=1, SL=4, mode=2),
+                                 dict(mode=2, K=2), dict(M=2, SL=1, mode=2, K=4)])
 def test_burgers_matches_reference_golden(cfg):
     from gptpinn import sweep
     g = load_golden("b_small")
@@ -54,7 +55,8 @@ def test_burgers_matches_reference_golden(cfg):
         assert abs(float(L) - float(g[f"n{n}_L"])) <= TOL * float(L)
 
 
-@pytest.mark.parametrize("cfg", [None, dict(mode=1), dict(mode=2), dict(M=2, SL=1, mode=1)])
+@pytest.mark.parametrize("cfg", [None, dict(mode=1), dict(mode=2), dict(M=2, SL=1, mode=1), dict(mode=2, K=4),
+                                 dict(M=1, SL=2, mode=2, K=8)])
 def test_allen_cahn_matches_reference_golden(cfg):
     from gptpinn import sweep
     from oracle import oracle

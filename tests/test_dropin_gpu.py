@@ -28,7 +28,9 @@ def test_kg_offline_generation_and_tests():
                                               d["IC_u1"], d["IC_u2"], d["BC_u"], d["xcos"], v["out"], v["out_xx"],
                                               v["out_tt"], v["out_IC"], v["out_IC_t"], v["out_BC"], d["f_hat"],
                                               int(g["epochs"]), lr_of(g, i))
-        assert tuple(case) == tuple(g[f"n{n}_case"])
+        iref = int(np.nonzero((g["grid"] == g[f"n{n}_case"]).all(1))[0][0])
+        idx = int(np.nonzero((g["grid"] == np.asarray(case)).all(1))[0][0])
+        assert selection_ok(g[f"n{n}_f"], iref, idx), n              # n = 1: two parameters tie to 1 ulp
         assert all(isinstance(x, np.float64) for x in case)
         assert abs(float(L) - float(g[f"n{n}_L"])) <= TOL * float(L)
         loss_list = np.zeros(1)

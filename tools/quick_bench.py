@@ -29,13 +29,21 @@ def main():
     BC_u = torch.randn(NB, 1, device="cuda", generator=g)
     a = np.linspace(-2, -1, na); b = np.linspace(0, 1, nb); gm = np.linspace(0, 1, ng)
     grid = np.array(np.meshgrid(a, b, gm)).T.reshape(-1, 3)
+    if os.environ.get("QB_SHARD"):          # "r/W": rank r's block of the (alpha, beta)-sorted grid, as offline.sharded_sweep cuts it
+        r_, w_ = (int(x) for x in os.environ["QB_SHARD"].split("/"))
+        order = np.lexsort((grid[:, 1], grid[:, 0]))
+        base, rem = divmod(len(grid), w_)
+        lo = r_ * base + min(r_, rem)
+        grid = grid[order[lo:lo + base + (1 if r_ < rem else 0)]]
     c0 = torch.full((n,), 1.0 / n, device="cuda")
     tf = C.c_double()
     _lib.check(_lib.lib().gptpinn_ffma_peak(C.byref(tf), 3, None), "peak")
     print("FFMA peak measured TFLOP/s:", tf.value, flush=True)
     W_n = 8 * n * NR + 4 * n * (NB + 2 * NI)
-    cfgs = [None] + [dict(M=int(m), SL=int(s), W=int(w), mode=int(md)) for m, s, w, md in
-                     (c.split(":") for c in os.environ.get("QB_CFGS", "5:8:8:1,5:8:8:2,5:0:8:2,5:4:8:2,4:8:8:2,2:0:16:2").split(","))]
+    def parse(c):
+        v = [int(x) for x in c.split(":")] + [0] * 5
+        return dict(M=v[0], SL=v[1], W=v[2], mode=v[3], K=v[4])
+    cfgs = [None] + [parse(c) for c in os.environ.get("QB_CFGS", "5:8:8:1,5:8:8:2,5:0:8:2,5:4:8:2,4:8:8:2,2:0:16:2").split(",")]
     for cfg in cfgs:
         def run():
             return sweep.kg_sweep(grid, c0, out[:, :n], out_xx[:, :n], out_tt[:, :n], out_IC[:, :n], out_IC_t[:, :n],
