@@ -198,7 +198,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--epochs", type=int, default=2000)
     ap.add_argument("--grid", default="50,50,40")
-    ap.add_argument("--cfg", default="", help="M:SL:W:mode override of the kernel mapping (tuning)")
+    ap.add_argument("--cfg", default="", help="M:SL:W:mode[:K] override of the kernel mapping (tuning)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -265,8 +265,8 @@ def main():
     c0 = torch.full((N_NEURONS,), 1.0 / N_NEURONS, device=device)
     cfg = None
     if args.cfg:
-        m_, sl_, w_, md_ = (int(x) for x in args.cfg.split(":"))
-        cfg = dict(M=m_, SL=sl_, W=w_, mode=md_)
+        v_ = [int(x) for x in args.cfg.split(":")] + [0] * 5
+        cfg = dict(M=v_[0], SL=v_[1], W=v_[2], mode=v_[3], K=v_[4])
 
     tf = C.c_double()
     _lib.check(_lib.lib().gptpinn_ffma_peak(C.byref(tf), 3, None), "gptpinn_ffma_peak")
