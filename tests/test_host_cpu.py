@@ -162,3 +162,32 @@ def test_grid_sharding_world2_gloo():
         p.join(60)
     assert all(ok for _, ok, _ in out)
     assert len({idx for _, _, idx in out}) == 1
+
+
+def test_planner_assigns_every_parameter_once():
+    """Host-only planner (no GPU): whatever the grid shape, mapping override or team size, every parameter lands in
+    exactly one work item, teams divide the CTA, and the configuration fits one SM."""
+    from gptpinn import _lib
+    rng = np.random.default_rng(3)
+    a = np.linspace(-2, -1, 50); b = np.linspace(0, 1, 50); gm = np.linspace(0, 1, 40)
+    big = np.array(np.meshgrid(a, b, gm)).T.reshape(-1, 3)
+    order = np.lexsort((big[:, 1], big[:, 0]))
+    grids = {"config4": big, "shard_1_of_8": big[order[12500:25000]], "default": big[::100],
+             "ragged": np.column_stack([rng.integers(0, 7, 333) * 0.1, rng.integers(0, 3, 333) * 0.5, rng.random(333)]),
+             "one_group": np.column_stack([np.full(500, -1.5), np.full(500, 0.5), rng.random(500)]),
+             "all_distinct": rng.random((257, 3)), "single": np.array([[-1.5, 0.5, 0.5]])}
+    for name, grid in grids.items():
+        for cfg in (None, dict(K=1), dict(mode=2, K=2), dict(mode=2, K=8), dict(mode=1), dict(M=4), dict(M=1, mode=2, K=4)):
+            for n in (1, 15):
+                try:
+                    d = _lib.kg_plan(grid, n, cfg=cfg)
+                except _lib.GptPinnError:
+                    assert cfg and cfg.get("K", 0) > 1, (name, cfg, n)      # a forced team size may be infeasible, nothing else
+                    continue
+                assert d["covered"] == len(grid), (name, cfg, n)
+                assert d["W"] % d["K"] == 0 and 1 <= d["ctas"] <= 148, (name, cfg, n, d)
+                assert sum(d["sl_hist"].values()) == d["items"]
+                if cfg and "K" in cfg and d["priv"]:
+                    assert d["K"] == cfg["K"]
+    shard = _lib.kg_plan(grids["shard_1_of_8"], 15)
+    assert shard["priv"] == 1 and shard["K"] == 8          # 313 sibling groups for 1184 warps: whole CTAs team up

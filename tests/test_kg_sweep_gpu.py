@@ -182,3 +182,45 @@ def test_kg_dense_rows_config5_properties():
     r2 = _run(d2, n, grid, 6, 0.01)
     assert rel_scalar(r2["f"].cpu().numpy(), r["f"].cpu().numpy()) < TOL
     assert rel_vec(r2["c"].cpu().numpy(), r["c"].cpu().numpy()) < TOL
+
+
+def test_kg_config4_grid_properties():
+    """The full 10^5-parameter grid of BASELINE config 4 (few epochs): results do not depend on the order of the
+    grid rows (bitwise: the same sibling sets land in the same work items), on the team size, or on how the grid
+    is cut into per-rank shards; a random sample of parameters is checked against the f64 oracle."""
+    from gptpinn import offline
+    from oracle import oracle
+    g = load_golden("kg_full")
+    d = _dev(g, KG_NAMES)
+    n, epochs, lr = 15, 3, 0.025
+    a = np.linspace(-2, -1, 50); b = np.linspace(0, 1, 50); gm = np.linspace(0, 1, 40)
+    grid = np.array(np.meshgrid(a, b, gm)).T.reshape(-1, 3)
+    r = _run(d, n, grid, epochs, lr)
+    f, m, c = (r[k].cpu().numpy() for k in ("f", "m", "c"))
+    assert np.isfinite(f).all() and (m >= 0).all()
+    # (1) permutation of the grid rows
+    rng = np.random.default_rng(7)
+    perm = rng.permutation(len(grid))
+    rp = _run(d, n, grid[perm], epochs, lr)
+    assert np.array_equal(rp["f"].cpu().numpy(), f[perm])
+    assert np.array_equal(rp["c"].cpu().numpy(), c[perm])
+    # (2) independent warps vs teams of 4 warps vs the shared ring: different summation trees only
+    for cfg in (dict(mode=2, K=1), dict(mode=2, K=4, M=5), dict(mode=1)):
+        rk = _run(d, n, grid, epochs, lr, cfg=cfg)
+        assert rel_scalar(rk["f"].cpu().numpy(), f) < TOL, cfg
+        assert rel_vec(rk["c"].cpu().numpy(), c) < TOL, cfg
+    # (3) the 8-way shard of rank 3, as offline.sharded_sweep cuts it
+    order = np.lexsort((grid[:, 1], grid[:, 0]))
+    lo, hi = offline.shard_bounds(len(grid), 3, 8)
+    rows = order[lo:hi]
+    rs = _run(d, n, grid[rows], epochs, lr)
+    assert rs["info"]["K"] > 1                                  # few items per warp: the planner forms teams
+    assert rel_scalar(rs["f"].cpu().numpy(), f[rows]) < TOL
+    assert rel_vec(rs["c"].cpu().numpy(), c[rows]) < TOL
+    # (4) sample vs the oracle
+    pick = rng.choice(len(grid), 48, replace=False)
+    pr = oracle.kg_problem(n, *(g[k] for k in KG_NAMES))
+    o = oracle.sweep("kg", pr, grid[pick], np.full(n, 1.0 / n, np.float32), epochs, lr, 0, "f64")
+    assert rel_scalar(f[pick], o["f"]) < TOL
+    assert rel_scalar(m[pick], o["m"]) < TOL
+    assert rel_vec(c[pick], o["c"]) < TOL
