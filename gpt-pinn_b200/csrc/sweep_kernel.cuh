@@ -25,9 +25,6 @@
 //           the current row retire (software pipelining; no extra registers).
 #pragma once
 #include "common.cuh"
-#ifndef GP_FWD_VARIANT
-#define GP_FWD_VARIANT 0
-#endif
 #ifndef GP_REGT_MAX_SL
 #define GP_REGT_MAX_SL 2
 #endif
@@ -466,27 +463,15 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                             // P chains together (P[k] stays in the operand-reuse cache across the M parameters) and the
                             // M T chains together, instead of pairing u/t FFMAs that both fetch c, P[k] and T[k] from
                             // the register file (3 register-file reads = a 2-cycle dispatch on this part).
-#if GP_FWD_VARIANT == 0
                             float uu[M];
 #pragma unroll
                             for (int m = 0; m < M; ++m) uu[m] = dotn<N>(Pv, c[m], 0.f);
-#endif
 #pragma unroll
                             for (int m = 0; m < M; ++m) {
-#if GP_FWD_VARIANT == 0
                                 const float u = uu[m];
-#else
-                                const float u = dotn<N>(Pv, c[m], 0.f);
-#endif
                                 float d, nl;
-#if GP_FWD_VARIANT == 2
-                                const float tl = dotn<N>(Tv, c[m], Tv[N]);
-                                if constexpr (PDE == PDE_KG) { d = fmaf(sp0[m], u * u, tl); nl = sp1[m] * u; }
-                                else { const float u2 = u * u; d = fmaf(sp0[m], u2 * u, tl); nl = sp1[m] * u2; }
-#else
                                 if constexpr (PDE == PDE_KG) { d = dotn<N>(Tv, c[m], fmaf(sp0[m], u * u, Tv[N])); nl = sp1[m] * u; }            // g*u^2 ; 2g*u
                                 else { const float u2 = u * u; d = dotn<N>(Tv, c[m], fmaf(sp0[m], u2 * u, Tv[N])); nl = sp1[m] * u2; }         // e*u^3 ; 3e*u^2
-#endif
                                 lacc[m] = fmaf(d, d, lacc[m]);
                                 first[m] = has_fhat ? d + fh : d;          // the update ignores fhat (N3)
                                 w2[m] = first[m] * nl;
