@@ -126,6 +126,18 @@ def aux_measurements(device, d):
     torch.cuda.synchronize()
     out["pinn_train_us_per_epoch"] = 1e3 * e0.elapsed_time(e1) / n_ep
     out["pinn_train_loss_after_1010_epochs"] = float(r["loss"])
+    # pinn_test's shape: 8 test parameters per cooperative launch
+    mus = [(-1.5 + 0.05 * k, 0.5, 0.5) for k in range(8)]
+    nets = [KG_models.NN(np.array([2, 40, 40, 1]), *mu, d["xcos"]).to(device) for mu in mus]
+    bargs = (nets, "kg", mus, d["xt_resid"], d["f_hat"], d["IC_xt"], d["IC_u1"], d["IC_u2"], d["BC_xt"], d["BC_u"])
+    pinn.train_fused_batch(*bargs, 10, 5e-4, xcos=d["xcos"])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    pinn.train_fused_batch(*bargs, n_ep // 2, 5e-4, xcos=d["xcos"])
+    e1.record()
+    torch.cuda.synchronize()
+    out["pinn_train_batch8_us_per_epoch_per_training"] = 1e3 * e0.elapsed_time(e1) / (n_ep // 2) / 8
     return out
 
 

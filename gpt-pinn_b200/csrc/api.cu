@@ -664,10 +664,14 @@ extern "C" int gptpinn_kg_plan(const double *grid_host, int Np, int n, int NR, i
     return GPTPINN_OK;
 }
 
-extern "C" int gptpinn_pinn_train(gptpinn_handle *h, const gptpinn_pinn_problem *q, const gptpinn_mlp *net,
-                                  const gptpinn_train_args *ta, float *status_dev, void *stream)
+extern "C" int gptpinn_pinn_train_batch(gptpinn_handle *h, int nbatch, const gptpinn_pinn_problem *qs, const gptpinn_mlp *nets,
+                                        const gptpinn_train_args *tas, float *status_dev, void *stream)
 {
-    if (!h || !q || !net || !ta || !status_dev) return fail(GPTPINN_E_INVALID, "gptpinn_pinn_train: NULL argument");
+    if (!h || !qs || !nets || !tas || !status_dev) return fail(GPTPINN_E_INVALID, "gptpinn_pinn_train: NULL argument");
+    if (nbatch < 1 || nbatch > PINN_MAX_BATCH) return fail(GPTPINN_E_INVALID, "nbatch = %d outside 1..%d", nbatch, PINN_MAX_BATCH);
+    const gptpinn_pinn_problem *q = &qs[0];
+    const gptpinn_mlp *net = &nets[0];
+    const gptpinn_train_args *ta = &tas[0];
     if (q->pde != GPTPINN_PDE_KG && q->pde != GPTPINN_PDE_BURGERS) return fail(GPTPINN_E_INVALID, "pde must be KG (0) or Burgers (1)");
     if (net->nlayers < 3 || net->nlayers > PINN_MAX_HIDDEN + 2) return fail(GPTPINN_E_UNSUPPORTED, "nlayers = %d outside 3..%d", net->nlayers, PINN_MAX_HIDDEN + 2);
     if (net->layers[0] != 2 || net->layers[net->nlayers - 1] != 1) return fail(GPTPINN_E_INVALID, "network must map 2 inputs to 1 output");
@@ -675,6 +679,19 @@ extern "C" int gptpinn_pinn_train(gptpinn_handle *h, const gptpinn_pinn_problem 
     if (!q->xt_resid || !q->IC_xt || !q->IC_u1 || !q->BC_xt || !q->BC_u) return fail(GPTPINN_E_INVALID, "point sets and targets are required");
     if (q->pde == GPTPINN_PDE_KG && !q->xcos) return fail(GPTPINN_E_INVALID, "xcos is required for Klein-Gordon");
     if (ta->epochs < 0) return fail(GPTPINN_E_INVALID, "epochs < 0");
+    for (int t = 1; t < nbatch; ++t) {          // one launch = one network shape, one set of points, one schedule
+        const gptpinn_pinn_problem &o = qs[t];
+        if (o.pde != q->pde || o.NR != q->NR || o.NI != q->NI || o.NB != q->NB || o.xt_resid != q->xt_resid || o.IC_xt != q->IC_xt ||
+            o.BC_xt != q->BC_xt || o.f_hat != q->f_hat || o.xcos != q->xcos || o.IC_u1 != q->IC_u1 || o.IC_u2 != q->IC_u2 || o.BC_u != q->BC_u)
+            return fail(GPTPINN_E_INVALID, "batched trainings must share the point sets and targets (training %d differs)", t);
+        if (nets[t].nlayers != net->nlayers || nets[t].act != net->act) return fail(GPTPINN_E_INVALID, "batched trainings must share the network shape");
+        for (int l = 0; l < net->nlayers; ++l)
+            if (nets[t].layers[l] != net->layers[l]) return fail(GPTPINN_E_INVALID, "batched trainings must share the network shape");
+        const gptpinn_train_args &u = tas[t];
+        if (u.epochs != ta->epochs || u.lr != ta->lr || u.beta1 != ta->beta1 || u.beta2 != ta->beta2 || u.eps != ta->eps || u.tol != ta->tol ||
+            u.trace_every != ta->trace_every)
+            return fail(GPTPINN_E_INVALID, "batched trainings must share epochs, Adam settings, tolerance and trace stride");
+    }
     cudaStream_t st = (cudaStream_t)stream;
     int dev = -1;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -691,13 +708,11 @@ extern "C" int gptpinn_pinn_train(gptpinn_handle *h, const gptpinn_pinn_problem 
         d.layers[l] = net->layers[l];
         if (d.layers[l] < 1 || d.layers[l] > 40) return fail(GPTPINN_E_UNSUPPORTED, "layer width %d outside 1..40", d.layers[l]);
     }
-    for (int l = 0; l < net->nlayers - 1; ++l) {
-        if (!net->W[l] || !net->b[l]) return fail(GPTPINN_E_INVALID, "W[%d] or b[%d] is NULL", l, l);
-        P += d.layers[l] * d.layers[l + 1] + d.layers[l + 1];
-    }
+    for (int t = 0; t < nbatch; ++t)
+        for (int l = 0; l < net->nlayers - 1; ++l)
+            if (!nets[t].W[l] || !nets[t].b[l]) return fail(GPTPINN_E_INVALID, "W[%d] or b[%d] of training %d is NULL", l, l, t);
+    for (int l = 0; l < net->nlayers - 1; ++l) P += d.layers[l] * d.layers[l + 1] + d.layers[l + 1];
     d.n_params = P;
-    if (q->pde == GPTPINN_PDE_KG) { d.pa = (float)q->p0; d.pb = (float)q->p1; d.pc = (float)q->p2; }
-    else { d.pa = (float)(-q->p0); d.pb = 0.f; d.pc = 0.f; }
     d.NR = q->NR; d.NI = q->NI; d.NB = q->NB;
     d.xt_resid = q->xt_resid; d.IC_xt = q->IC_xt; d.BC_xt = q->BC_xt; d.f_hat = q->f_hat; d.xcos = q->xcos;
     d.IC_u1 = q->IC_u1; d.IC_u2 = q->IC_u2; d.BC_u = q->BC_u;
@@ -706,38 +721,59 @@ extern "C" int gptpinn_pinn_train(gptpinn_handle *h, const gptpinn_pinn_problem 
     d.lr = (float)ta->lr; d.beta1 = (float)ta->beta1; d.beta2 = (float)ta->beta2;
     d.omb1 = (float)(1.0 - ta->beta1); d.omb2 = (float)(1.0 - ta->beta2); d.eps = (float)ta->eps;
     d.tol = ta->tol >= 0 ? (float)ta->tol : -1.f;
-    d.loss_trace = ta->trace_every > 0 ? ta->loss_trace_dev : nullptr;
     d.trace_every = ta->trace_every;
-    d.grad_out = ta->grad_out_dev;
 
-    int blocks = 0, n_partials = 0;
+    int blocks = 0, group = 0;
     size_t smem = 0;
-    CUDA_TRY(plan_pinn_train(d, h->n_sm, &blocks, &smem, &n_partials));
+    CUDA_TRY(plan_pinn_train(d, h->n_sm, nbatch, &blocks, &smem, &group));
     const int stride = (P + 4 + 31) & ~31;
-    const size_t need = ((size_t)3 * P + (size_t)n_partials * stride + 64) * sizeof(float);
+    const int P4 = (P + 3) & ~3;
+    const size_t per = (size_t)3 * P4 + (size_t)group * stride;                       // floats per training
+    const size_t need = (per * nbatch + 64) * sizeof(float);
     int rc = ensure(&h->train_ws, &h->train_cap, need);
     if (rc) return rc;
     float *ws = (float *)h->train_ws;
-    d.params = ws; d.adam_m = ws + P; d.adam_v = ws + 2 * P;
-    d.partials = ws + 3 * P; d.n_partials = n_partials; d.partial_stride = stride;
-    float *tail = d.partials + (size_t)n_partials * stride;
+    d.n_partials = group; d.partial_stride = stride;
+    float *tail = ws + per * nbatch;
     d.stop = (int *)tail;
-    d.status = status_dev;
-    CUDA_TRY(cudaMemsetAsync(ws + P, 0, (size_t)2 * P * sizeof(float), st));            // fresh optimizer state
+    PinnBatch bt;
+    memset(&bt, 0, sizeof(bt));
+    bt.n = nbatch; bt.group = group;
     CUDA_TRY(cudaMemsetAsync(tail, 0, 64 * sizeof(float), st));
-    CUDA_TRY(cudaMemsetAsync(status_dev, 0, 2 * sizeof(float), st));
-    int off = 0;
-    for (int l = 0; l < net->nlayers - 1; ++l) {                                        // pack: W then b, layer after layer
-        const int nw = d.layers[l] * d.layers[l + 1], nb = d.layers[l + 1];
-        CUDA_TRY(cudaMemcpyAsync(ws + off, net->W[l], nw * sizeof(float), cudaMemcpyDeviceToDevice, st)); off += nw;
-        CUDA_TRY(cudaMemcpyAsync(ws + off, net->b[l], nb * sizeof(float), cudaMemcpyDeviceToDevice, st)); off += nb;
+    CUDA_TRY(cudaMemsetAsync(status_dev, 0, (size_t)2 * nbatch * sizeof(float), st));
+    for (int t = 0; t < nbatch; ++t) {
+        PinnTrainee &T = bt.t[t];
+        float *base = ws + per * t;
+        T.params = base; T.adam_m = base + P4; T.adam_v = base + 2 * P4; T.partials = base + 3 * P4;
+        T.status = status_dev + 2 * t;
+        T.grad_out = tas[t].grad_out_dev;
+        T.loss_trace = ta->trace_every > 0 ? tas[t].loss_trace_dev : nullptr;
+        if (q->pde == GPTPINN_PDE_KG) { T.pa = (float)qs[t].p0; T.pb = (float)qs[t].p1; T.pc = (float)qs[t].p2; }
+        else { T.pa = (float)(-qs[t].p0); T.pb = 0.f; T.pc = 0.f; }
+        CUDA_TRY(cudaMemsetAsync(T.adam_m, 0, (size_t)2 * P4 * sizeof(float), st));      // fresh optimizer state
+        int off = 0;
+        for (int l = 0; l < net->nlayers - 1; ++l) {                                     // pack: W then b, layer after layer
+            const int nw = d.layers[l] * d.layers[l + 1], nb = d.layers[l + 1];
+            CUDA_TRY(cudaMemcpyAsync(base + off, nets[t].W[l], nw * sizeof(float), cudaMemcpyDeviceToDevice, st)); off += nw;
+            CUDA_TRY(cudaMemcpyAsync(base + off, nets[t].b[l], nb * sizeof(float), cudaMemcpyDeviceToDevice, st)); off += nb;
+        }
     }
-    if (ta->epochs > 0) CUDA_TRY(launch_pinn_train(d, blocks, smem, st));
-    off = 0;
-    for (int l = 0; l < net->nlayers - 1; ++l) {                                        // unpack into the caller's tensors
-        const int nw = d.layers[l] * d.layers[l + 1], nb = d.layers[l + 1];
-        CUDA_TRY(cudaMemcpyAsync((void *)net->W[l], ws + off, nw * sizeof(float), cudaMemcpyDeviceToDevice, st)); off += nw;
-        CUDA_TRY(cudaMemcpyAsync((void *)net->b[l], ws + off, nb * sizeof(float), cudaMemcpyDeviceToDevice, st)); off += nb;
+    if (ta->epochs > 0) CUDA_TRY(launch_pinn_train(d, bt, blocks, smem, st));
+    for (int t = 0; t < nbatch; ++t) {
+        const float *base = ws + per * t;
+        int off = 0;
+        for (int l = 0; l < net->nlayers - 1; ++l) {                                     // unpack into the caller's tensors
+            const int nw = d.layers[l] * d.layers[l + 1], nb = d.layers[l + 1];
+            CUDA_TRY(cudaMemcpyAsync((void *)nets[t].W[l], base + off, nw * sizeof(float), cudaMemcpyDeviceToDevice, st)); off += nw;
+            CUDA_TRY(cudaMemcpyAsync((void *)nets[t].b[l], base + off, nb * sizeof(float), cudaMemcpyDeviceToDevice, st)); off += nb;
+        }
     }
     return GPTPINN_OK;
+}
+
+extern "C" int gptpinn_pinn_train(gptpinn_handle *h, const gptpinn_pinn_problem *q, const gptpinn_mlp *net,
+                                  const gptpinn_train_args *ta, float *status_dev, void *stream)
+{
+    if (!q || !net || !ta) return fail(GPTPINN_E_INVALID, "gptpinn_pinn_train: NULL argument");
+    return gptpinn_pinn_train_batch(h, 1, q, net, ta, status_dev, stream);
 }

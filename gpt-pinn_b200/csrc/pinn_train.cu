@@ -77,8 +77,14 @@ __device__ __forceinline__ void act_backward(int act, const float (&z)[CH], cons
 
 // WMAX: widest hidden layer (all hidden layers are padded to it), NH: hidden layers (KG 2, Burgers 4)
 template <int WMAX, int NH>
-__global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d)
+__global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d, const PinnBatch bt)
 {
+    // this CTA's training: group `tr` of the grid, local CTA index `lb`; CTAs beyond n * group only keep the barriers
+    const int gsz = bt.group;
+    const int tr = (int)blockIdx.x / gsz, lb = (int)blockIdx.x % gsz;
+    const bool member = tr < bt.n;
+    const PinnTrainee &T = bt.t[member ? tr : 0];
+    bool done = !member;                                     // this training has met its tolerance (or the CTA is a spare)
     constexpr int GJ = WMAX / NG;                            // neurons per warp (10 / 5)
     constexpr int GJP = (GJ + 3) & ~3;                       // padded to a float4 multiple (12 / 8)
     constexpr int TJ = (WMAX + TJG - 1) / TJG, TI = (WMAX + TIG - 1) / TIG;
@@ -113,8 +119,9 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
     const int ntiles = tilesR + tilesI + tilesB;
 
     for (int epoch = 1; epoch <= d.epochs; ++epoch) {
+      if (!done) {
         // -------------------------------------------------------------- phase 1
-        for (int i = threadIdx.x; i < P; i += blockDim.x) { w_s[i] = d.params[i]; g_s[i] = 0.f; }
+        for (int i = threadIdx.x; i < P; i += blockDim.x) { w_s[i] = T.params[i]; g_s[i] = 0.f; }
         __syncthreads();
         for (int l = 1; l < NH; ++l) {                       // padded copies of the hidden->hidden matrices
             const float *W = w_s + woff[l];
@@ -137,7 +144,7 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
 #pragma unroll
                 for (int b = 0; b < TI; ++b) wacc[l][a][b] = 0.f;
 
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int tile = lb; tile < ntiles; tile += gsz) {
             int kind, p;                              // 0 residual, 1 IC, 2 BC
             if (tile < tilesR) { kind = 0; p = tile * PT + lane; }
             else if (tile < tilesR + tilesI) { kind = 1; p = (tile - tilesR) * PT + lane; }
@@ -231,13 +238,13 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
                 if (kind == 0) {
                     const float fh = d.f_hat ? d.f_hat[p] : 0.f;
                     float f;
-                    if (d.pde == 0) f = u[4] + d.pa * u[3] + d.pb * u[0] + d.pc * u[0] * u[0] + d.xcos[p];   // KG_models.py:104-107
-                    else f = u[2] + (u[0] * u[1] + d.pa * u[3]);                                          // B_models.py:91-94, pa = -nu
+                    if (d.pde == 0) f = u[4] + T.pa * u[3] + T.pb * u[0] + T.pc * u[0] * u[0] + d.xcos[p];   // KG_models.py:104-107
+                    else f = u[2] + (u[0] * u[1] + T.pa * u[3]);                                          // B_models.py:91-94, pa = -nu
                     const float e = f - fh;
                     lossR = fmaf(e, e, lossR);
                     const float eb = 2.f * e * d.invR;
-                    if (d.pde == 0) { ub[4] = eb; ub[3] = d.pa * eb; ub[0] = (d.pb + 2.f * d.pc * u[0]) * eb; }
-                    else { ub[2] = eb; ub[0] = u[1] * eb; ub[1] = u[0] * eb; ub[3] = d.pa * eb; }
+                    if (d.pde == 0) { ub[4] = eb; ub[3] = T.pa * eb; ub[0] = (T.pb + 2.f * T.pc * u[0]) * eb; }
+                    else { ub[2] = eb; ub[0] = u[1] * eb; ub[1] = u[0] * eb; ub[3] = T.pa * eb; }
                 } else if (kind == 1) {
                     const float e1 = u[0] - d.IC_u1[p];
                     lossI1 = fmaf(e1, e1, lossI1);
@@ -395,21 +402,23 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
                 lossB += __shfl_xor_sync(0xffffffffu, lossB, off);
             }
         }
-        if ((int)blockIdx.x < d.n_partials) {
-            float *dst = d.partials + (size_t)blockIdx.x * d.partial_stride;
+        {
+            float *dst = T.partials + (size_t)lb * d.partial_stride;
             for (int i = threadIdx.x; i < P; i += blockDim.x) dst[i] = g_s[i];
             if (threadIdx.x == 0) { dst[P] = lossR; dst[P + 1] = lossI1; dst[P + 2] = lossI2; dst[P + 3] = lossB; }
         }
+      }   // !done
         grid.sync();
+      if (!done) {
 
         // -------------------------------------------------------------- phase 2: reduce, tolerance, Adam
         // every block reduces the four loss sums itself (same order everywhere => the same stop decision
         // on every block, no extra grid barrier)
         if (warp == 0) {
             float s[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int w = lane; w < d.n_partials; w += 32)
+            for (int w = lane; w < gsz; w += 32)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) s[k] += d.partials[(size_t)w * d.partial_stride + P + k];
+                for (int k = 0; k < 4; ++k) s[k] += T.partials[(size_t)w * d.partial_stride + P + k];
             for (int off = 16; off; off >>= 1)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) s[k] += __shfl_xor_sync(0xffffffffu, s[k], off);
@@ -418,10 +427,10 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
                 if (d.pde == 0) loss += s[2] * d.invI;
                 loss += s[3] * d.invB;
                 U_s[0] = loss;
-                if (blockIdx.x == 0) {
-                    d.status[0] = loss;                                   // loss of the weights BEFORE this epoch's step
-                    d.status[1] = __int_as_float(epoch);
-                    if (d.loss_trace && d.trace_every > 0 && (epoch - 1) % d.trace_every == 0) d.loss_trace[(epoch - 1) / d.trace_every] = loss;
+                if (lb == 0) {
+                    T.status[0] = loss;                                   // loss of the weights BEFORE this epoch's step
+                    T.status[1] = __int_as_float(epoch);
+                    if (T.loss_trace && d.trace_every > 0 && (epoch - 1) % d.trace_every == 0) T.loss_trace[(epoch - 1) / d.trace_every] = loss;
                 }
             }
         }
@@ -433,28 +442,33 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
             const float step_size = (float)((double)d.lr / bc1);
             const float bc2_sqrt = (float)sqrt(bc2);
             // gradient reduction: 8 lanes per parameter, fixed order (deterministic), then torch.optim.Adam
-            const int gthreads = gridDim.x * blockDim.x;
+            const int gthreads = gsz * blockDim.x;
             const int sub = threadIdx.x & 7;
-            const int gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, ngroups = gthreads >> 3;
+            const int gid = (lb * blockDim.x + threadIdx.x) >> 3, ngroups = gthreads >> 3;
             for (int i0 = 0; i0 < P; i0 += ngroups) {                     // same trip count on every thread (shuffles below)
                 const int i = i0 + gid;
                 float gs = 0.f;
                 if (i < P)
-                    for (int w = sub; w < d.n_partials; w += 8) gs += d.partials[(size_t)w * d.partial_stride + i];
+                    for (int w = sub; w < gsz; w += 8) gs += T.partials[(size_t)w * d.partial_stride + i];
                 gs += __shfl_xor_sync(0xffffffffu, gs, 1);
                 gs += __shfl_xor_sync(0xffffffffu, gs, 2);
                 gs += __shfl_xor_sync(0xffffffffu, gs, 4);
                 if (sub == 0 && i < P) {
-                    if (d.grad_out) d.grad_out[i] = gs;
-                    const float m = d.adam_m[i] = d.adam_m[i] + (gs - d.adam_m[i]) * d.omb1;          // exp_avg.lerp_(grad, 1 - beta1)
-                    const float v = d.adam_v[i] = fmaf(d.omb2 * gs, gs, d.beta2 * d.adam_v[i]);        // mul_(beta2).addcmul_(g, g, 1 - beta2)
+                    if (T.grad_out) T.grad_out[i] = gs;
+                    const float m = T.adam_m[i] = T.adam_m[i] + (gs - T.adam_m[i]) * d.omb1;          // exp_avg.lerp_(grad, 1 - beta1)
+                    const float v = T.adam_v[i] = fmaf(d.omb2 * gs, gs, d.beta2 * T.adam_v[i]);        // mul_(beta2).addcmul_(g, g, 1 - beta2)
                     const float denom = sqrtf(v) / bc2_sqrt + d.eps;
-                    d.params[i] = d.params[i] - step_size * (m / denom);
+                    T.params[i] = T.params[i] - step_size * (m / denom);
                 }
             }
         }
+        if (stop) {                                                       // this training is finished; the launch ends when all are
+            done = true;
+            if (lb == 0 && threadIdx.x == 0) atomicAdd(d.stop, 1);
+        }
+      }   // !done
         grid.sync();
-        if (stop) break;
+        if (*reinterpret_cast<volatile int *>(d.stop) >= bt.n) break;     // same value on every CTA: all increments precede the barrier
     }
 }
 
@@ -486,8 +500,9 @@ static size_t smem_bytes(const PinnDesc &d, const KernelPick &k)
     return fl * sizeof(float);
 }
 
-cudaError_t plan_pinn_train(const PinnDesc &d, int n_sm, int *blocks_out, size_t *smem_out, int *n_partials)
+cudaError_t plan_pinn_train(const PinnDesc &d, int n_sm, int nbatch, int *blocks_out, size_t *smem_out, int *group_out)
 {
+    if (nbatch < 1 || nbatch > PINN_MAX_BATCH) return cudaErrorInvalidValue;
     const KernelPick k = pick_kernel(d);
     if (!k.fn) return cudaErrorInvalidValue;
     const size_t smem = smem_bytes(d, k);
@@ -498,21 +513,24 @@ cudaError_t plan_pinn_train(const PinnDesc &d, int n_sm, int *blocks_out, size_t
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     const int tiles = (d.NR + PT - 1) / PT + (d.NI + PT - 1) / PT + (d.NB + PT - 1) / PT;
-    int blocks = tiles;
-    if (blocks > n_sm * per_sm) blocks = n_sm * per_sm;
-    if (blocks < 1) blocks = 1;
-    *blocks_out = blocks;
+    int group = (n_sm * per_sm) / nbatch;                 // CTAs per training: an equal share of the resident CTAs,
+    if (group > tiles) group = tiles;                     // never more than one CTA per tile,
+    if (group < 1) return cudaErrorInvalidConfiguration;
+    const int rounds = (tiles + group - 1) / group;       // and no more than the tile rounds need
+    group = (tiles + rounds - 1) / rounds;
+    *blocks_out = group * nbatch;
     *smem_out = smem;
-    *n_partials = blocks;
+    *group_out = group;
     return cudaSuccess;
 }
 
-cudaError_t launch_pinn_train(const PinnDesc &d, int blocks, size_t smem, cudaStream_t st)
+cudaError_t launch_pinn_train(const PinnDesc &d, const PinnBatch &b, int blocks, size_t smem, cudaStream_t st)
 {
     const KernelPick k = pick_kernel(d);
     if (!k.fn) return cudaErrorInvalidValue;
     PinnDesc dd = d;
-    void *args[] = {&dd};
+    PinnBatch bb = b;
+    void *args[] = {&dd, &bb};
     return cudaLaunchCooperativeKernel(k.fn, dim3(blocks), dim3(NG * 32), args, smem, st);
 }
 

@@ -30,7 +30,26 @@ struct PinnDesc {
     float *loss_trace; int trace_every;       // optional: loss before the step of epochs 1, 1+k, ...
 };
 
-cudaError_t plan_pinn_train(const PinnDesc &d, int n_sm, int *blocks, size_t *smem, int *n_partials);
-cudaError_t launch_pinn_train(const PinnDesc &d, int blocks, size_t smem, cudaStream_t st);
+// Several independent trainings (same network shape, point sets and schedule; own weights and PDE parameters) can
+// share one cooperative launch: the grid is cut into `n` equal groups of CTAs, one training per group, and the two
+// grid-wide barriers of an epoch are shared.  One training leaves the last tile round of an epoch mostly empty
+// (361 tiles on 296 resident CTAs at the KG sizes); a batch fills it.
+constexpr int PINN_MAX_BATCH = 8;
+struct PinnTrainee {
+    float pa, pb, pc;
+    float *params, *adam_m, *adam_v, *grad_out;
+    float *partials;                          // [group CTAs][partial_stride]
+    float *status;                            // [2]
+    float *loss_trace;
+};
+struct PinnBatch {
+    int n;                                    // trainings in this launch (1..PINN_MAX_BATCH)
+    int group;                                // CTAs per training
+    PinnTrainee t[PINN_MAX_BATCH];
+};
+
+// blocks = CTAs of the whole launch; group = CTAs per training (= partial rows per training)
+cudaError_t plan_pinn_train(const PinnDesc &d, int n_sm, int nbatch, int *blocks, size_t *smem, int *group);
+cudaError_t launch_pinn_train(const PinnDesc &d, const PinnBatch &b, int blocks, size_t smem, cudaStream_t st);
 
 }  // namespace gp

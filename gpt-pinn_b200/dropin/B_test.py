@@ -14,6 +14,7 @@ from B_train import initial_coefficients
 from _common import offline, pinn, sweep
 
 device = torch.device("cuda")
+PINN_BATCH = 8          # test parameters per training launch (1..8)
 
 
 def _c0(nu_train, neurons, neuron_cnt, dev):
@@ -50,20 +51,31 @@ def gpt_test_loss(nu_train, xt_size, IC_size, BC_size, IC_u, BC_u, out,
     return losses
 
 
+def _chunks(n):
+    """Test parameters trained together in one launch (gptpinn_pinn_train_batch): as few launches as PINN_BATCH allows,
+    of near-equal size (25 parameters -> 7, 6, 6, 6)."""
+    b = max(1, min(pinn.MAX_BATCH, PINN_BATCH))
+    k = max(1, -(-n // b))
+    cuts = [round(i * n / k) for i in range(k + 1)]
+    return [(cuts[i], cuts[i + 1]) for i in range(k) if cuts[i + 1] > cuts[i]]
+
+
 def pinn_test(b_test, layers_pinn, xt_resid, IC_xt, IC_u, BC_xt, BC_u, f_hat,
               epochs_pinn, lr_pinn, xt_test, tol):
-    """One tolerance-stopped full PINN per test parameter (B_test.py:116-149), fused training kernel;
-    under torch.distributed each rank trains a contiguous block of the parameters."""
+    """One tolerance-stopped full PINN per test parameter (B_test.py:116-149), fused training kernel, several
+    parameters per launch; under torch.distributed each rank trains a contiguous block of the parameters."""
     b_test = np.asarray(b_test, dtype=np.float64).reshape(-1)
     t0 = time.time()
     lo, hi = offline.shard_bounds(len(b_test))
+    mine = b_test[lo:hi]
     local = torch.zeros((hi - lo, xt_test.shape[0]), dtype=torch.float32, device=xt_test.device)
-    for k, nu in enumerate(b_test[lo:hi]):
-        PINN = NN(layers_pinn, nu).to(device)
-        pinn.train_fused(PINN, "burgers", (nu,), xt_resid, f_hat, IC_xt, IC_u, None, BC_xt, BC_u,
-                         epochs_pinn, lr_pinn, tol=tol)
+    for a, b in _chunks(len(mine)):
+        nets = [NN(layers_pinn, mine[k]).to(device) for k in range(a, b)]
+        pinn.train_fused_batch(nets, "burgers", [(mine[k],) for k in range(a, b)], xt_resid, f_hat, IC_xt, IC_u, None,
+                               BC_xt, BC_u, epochs_pinn, lr_pinn, tol=tol)
         with torch.no_grad():
-            local[k] = PINN(xt_test)[:, 0]
+            for k, net in zip(range(a, b), nets):
+                local[k] = net(xt_test)[:, 0]
     pinn_soln = offline.gather_rows(local, len(b_test)).t().cpu().numpy().astype(np.float64)
     return offline.spread_hours(time.time() - t0, len(b_test)), pinn_soln
 
@@ -75,21 +87,23 @@ def pinn_test_loss(b_test, layers_pinn, xt_resid, IC_xt, IC_u, BC_xt, BC_u,
     loss goes into the first still-zero slot."""
     b_test = np.asarray(b_test, dtype=np.float64).reshape(-1)
     lo, hi = offline.shard_bounds(len(b_test))
+    mine = b_test[lo:hi]
     local = np.zeros((hi - lo, 61))
-    for k, nu in enumerate(b_test[lo:hi]):
-        PINN = NN(layers_pinn, nu).to(device)
-        r = pinn.train_fused(PINN, "burgers", (nu,), xt_resid, f_hat, IC_xt, IC_u, None, BC_xt, BC_u,
-                             epochs_pinn, lr_pinn, tol=tol, trace_every=1)
-        done = pinn.epochs_done(r)                                   # iterations entered
-        tr = r["trace"].cpu().numpy().astype(np.float64)             # tr[j-1] = loss at the top of iteration j
-        col = local[k]
-        if done >= 1:
-            col[0] = tr[0]
-        stopped = tol is not None and done >= 1 and tr[done - 1] < tol
-        for j in range(1, done + 1):
-            if (j % 1000 == 0) or (j == epochs_pinn):
-                col[int(j / 1000)] = tr[j - 1]
-        if stopped:
-            col[np.where(col == 0)[0][0]] = tr[done - 1]
+    for a, b in _chunks(len(mine)):
+        nets = [NN(layers_pinn, mine[k]).to(device) for k in range(a, b)]
+        res = pinn.train_fused_batch(nets, "burgers", [(mine[k],) for k in range(a, b)], xt_resid, f_hat, IC_xt, IC_u, None,
+                                     BC_xt, BC_u, epochs_pinn, lr_pinn, tol=tol, trace_every=1)
+        for k, r in zip(range(a, b), res):
+            done = pinn.epochs_done(r)                                   # iterations entered
+            tr = r["trace"].cpu().numpy().astype(np.float64)             # tr[j-1] = loss at the top of iteration j
+            col = local[k]
+            if done >= 1:
+                col[0] = tr[0]
+            stopped = tol is not None and done >= 1 and tr[done - 1] < tol
+            for j in range(1, done + 1):
+                if (j % 1000 == 0) or (j == epochs_pinn):
+                    col[int(j / 1000)] = tr[j - 1]
+            if stopped:
+                col[np.where(col == 0)[0][0]] = tr[done - 1]
     out = offline.gather_rows(torch.from_numpy(local).to(xt_resid.device), len(b_test))
     return out.t().cpu().numpy().astype(np.float64)

@@ -14,6 +14,7 @@ from KG_models import NN
 from _common import offline, pinn, sweep
 
 device = torch.device("cuda")
+PINN_BATCH = 8          # test parameters per training launch (1..8): 38 us per Adam epoch and training at the KG sizes, 80 us alone
 
 
 def gpt_test(kg_test, out, out_xx, out_tt, out_IC, out_IC_t, out_BC, fhat,
@@ -47,20 +48,31 @@ def gpt_test_loss(kg_test, out, out_xx, out_tt, out_IC, out_IC_t, out_BC, fhat,
     return losses
 
 
+def _chunks(n):
+    """Test parameters trained together in one launch (gptpinn_pinn_train_batch): as few launches as PINN_BATCH allows,
+    of near-equal size (25 parameters -> 7, 6, 6, 6)."""
+    b = max(1, min(pinn.MAX_BATCH, PINN_BATCH))
+    k = max(1, -(-n // b))
+    cuts = [round(i * n / k) for i in range(k + 1)]
+    return [(cuts[i], cuts[i + 1]) for i in range(k) if cuts[i + 1] > cuts[i]]
+
+
 def pinn_test(kg_test, layers_pinn, xcos_x2cos2, xt_resid, IC_xt, IC_u1, IC_u2,
               BC_xt, BC_u, f_hat, epochs_pinn, lr_pinn, xt_test):
-    """One full PINN per test parameter (KG_test.py:81-111); the parameters are independent, so under
-    torch.distributed each rank trains a contiguous block of them and the solutions are all-gathered."""
+    """One full PINN per test parameter (KG_test.py:81-111); the parameters are independent, so several are trained
+    per launch, and under torch.distributed each rank trains a contiguous block of them (solutions all-gathered)."""
     kg_test = np.asarray(kg_test, dtype=np.float64).reshape(-1, 3)
     t0 = time.time()
     lo, hi = offline.shard_bounds(len(kg_test))
+    mine = kg_test[lo:hi]
     local = torch.zeros((hi - lo, xt_test.shape[0]), dtype=torch.float32, device=xt_test.device)
-    for k, (alpha, beta, gamma) in enumerate(kg_test[lo:hi]):
-        PINN = NN(layers_pinn, alpha, beta, gamma, xcos_x2cos2).to(device)
-        pinn.train_fused(PINN, "kg", (alpha, beta, gamma), xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u,
-                         epochs_pinn, lr_pinn, xcos=xcos_x2cos2)
+    for a, b in _chunks(len(mine)):
+        nets = [NN(layers_pinn, *mine[k], xcos_x2cos2).to(device) for k in range(a, b)]
+        pinn.train_fused_batch(nets, "kg", [tuple(mine[k]) for k in range(a, b)], xt_resid, f_hat, IC_xt, IC_u1, IC_u2,
+                               BC_xt, BC_u, epochs_pinn, lr_pinn, xcos=xcos_x2cos2)
         with torch.no_grad():
-            local[k] = PINN(xt_test)[:, 0]
+            for k, net in zip(range(a, b), nets):
+                local[k] = net(xt_test)[:, 0]
     soln = offline.gather_rows(local, len(kg_test))
     pinn_soln = soln.t().cpu().numpy().astype(np.float64)
     times = offline.spread_hours(time.time() - t0, len(kg_test))
@@ -72,15 +84,18 @@ def pinn_test_loss(kg_test, layers_pinn, xcos_x2cos2, xt_resid, IC_xt, IC_u1,
     """Loss after 0, 1000, 2000, ... steps and after the last step (KG_test.py:116-140), sharded like pinn_test."""
     kg_test = np.asarray(kg_test, dtype=np.float64).reshape(-1, 3)
     lo, hi = offline.shard_bounds(len(kg_test))
+    mine = kg_test[lo:hi]
     local = torch.zeros((hi - lo, 101), dtype=torch.float32, device=xt_resid.device)
-    for k, (alpha, beta, gamma) in enumerate(kg_test[lo:hi]):
-        PINN = NN(layers_pinn, alpha, beta, gamma, xcos_x2cos2).to(device)
+    for a, b in _chunks(len(mine)):
+        nets = [NN(layers_pinn, *mine[k], xcos_x2cos2).to(device) for k in range(a, b)]
+        mus = [tuple(mine[k]) for k in range(a, b)]
         # loss before the step of epochs 1, 1001, 2001, ... == loss after 0, 1000, 2000, ... steps
-        r = pinn.train_fused(PINN, "kg", (alpha, beta, gamma), xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u,
-                             epochs_pinn, lr_pinn, xcos=xcos_x2cos2, trace_every=1000)
-        tr = r["trace"]
-        local[k, :min(101, tr.numel())] = tr[:101]
-        final = pinn.train_fused(PINN, "kg", (alpha, beta, gamma), xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u,
-                                 1, 0.0, xcos=xcos_x2cos2)["loss"]          # lr = 0: evaluates the loss, leaves the weights
-        local[k, min(100, int(epochs_pinn / 1000))] = final
+        res = pinn.train_fused_batch(nets, "kg", mus, xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u,
+                                     epochs_pinn, lr_pinn, xcos=xcos_x2cos2, trace_every=1000)
+        fin = pinn.train_fused_batch(nets, "kg", mus, xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u,
+                                     1, 0.0, xcos=xcos_x2cos2)           # lr = 0: evaluates the loss, leaves the weights
+        for k, r, f in zip(range(a, b), res, fin):
+            tr = r["trace"]
+            local[k, :min(101, tr.numel())] = tr[:101]
+            local[k, min(100, int(epochs_pinn / 1000))] = f["loss"]
     return offline.gather_rows(local, len(kg_test)).t().cpu().numpy().astype(np.float64)

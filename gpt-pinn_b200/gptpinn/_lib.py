@@ -75,7 +75,8 @@ class TrainArgs(C.Structure):
 
 EXPORTS = ("gptpinn_version", "gptpinn_last_error", "gptpinn_create", "gptpinn_destroy",
            "gptpinn_kg_sweep", "gptpinn_b_sweep", "gptpinn_ac_sweep", "gptpinn_argmax_scan",
-           "gptpinn_mlp_channels", "gptpinn_ffma_peak", "gptpinn_kg_plan", "gptpinn_pinn_train")
+           "gptpinn_mlp_channels", "gptpinn_ffma_peak", "gptpinn_kg_plan", "gptpinn_pinn_train",
+           "gptpinn_pinn_train_batch")
 
 _lib = None
 
@@ -115,6 +116,9 @@ def lib():
     L.gptpinn_kg_plan.restype = C.c_int
     L.gptpinn_pinn_train.argtypes = [C.c_void_p, C.POINTER(PinnProblem), C.POINTER(Mlp), C.POINTER(TrainArgs), C.c_void_p, C.c_void_p]
     L.gptpinn_pinn_train.restype = C.c_int
+    L.gptpinn_pinn_train_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(PinnProblem), C.POINTER(Mlp), C.POINTER(TrainArgs),
+                                           C.c_void_p, C.c_void_p]
+    L.gptpinn_pinn_train_batch.restype = C.c_int
     _lib = L
     return L
 

@@ -28,15 +28,10 @@ def _vec(t, rows, name, keep):
     return t.data_ptr()
 
 
-def train_fused(model, pde, pde_params, xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u, epochs, lr,
-                xcos=None, tol=None, trace_every=0, want_grad=False, betas=(0.9, 0.999), eps=1e-8):
-    """Train `model` (an nn.Module with `.linears`, updated in place).  Returns dict(loss, epochs[, trace, grad]).
+MAX_BATCH = 8
 
-    loss = the last evaluated loss (the value the reference prints), as a 0-dim CUDA tensor (no sync here)."""
-    dev = xt_resid.device
-    if dev.type != "cuda":
-        raise _lib.GptPinnError("train_fused: tensors must live on the GPU (no CPU fallback)")
-    keep = []
+
+def _mlp_of(model):
     m = _lib.Mlp()
     lin = list(model.linears)
     m.nlayers = len(lin) + 1
@@ -51,38 +46,65 @@ def train_fused(model, pde, pde_params, xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC
         m.b[i] = layer.bias.data.data_ptr()
         n_params += layer.weight.numel() + layer.bias.numel()
     m.act = ACT[getattr(model, "activation_name", "tanh")]
+    return m, n_params
+
+
+def train_fused_batch(models, pde, pde_params_list, xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u, epochs, lr,
+                      xcos=None, tol=None, trace_every=0, want_grad=False, betas=(0.9, 0.999), eps=1e-8):
+    """Train up to MAX_BATCH models (same architecture, one PDE parameter tuple each) in ONE cooperative launch
+    (gptpinn_pinn_train_batch); the models are updated in place.  Returns one result dict per model, as train_fused."""
+    nb = len(models)
+    if nb < 1 or nb > MAX_BATCH or len(pde_params_list) != nb:
+        raise ValueError(f"need 1..{MAX_BATCH} models and as many parameter tuples")
+    dev = xt_resid.device
+    if dev.type != "cuda":
+        raise _lib.GptPinnError("train_fused: tensors must live on the GPU (no CPU fallback)")
+    keep = []
     NR, NI, NB = xt_resid.shape[0], IC_xt.shape[0], BC_xt.shape[0]
-    q = _lib.PinnProblem()
-    q.pde = PDE[pde]
-    pp = list(pde_params) + [0.0, 0.0, 0.0]
-    q.p0, q.p1, q.p2 = float(pp[0]), float(pp[1]), float(pp[2])
-    q.NR, q.NI, q.NB = NR, NI, NB
-    q.xt_resid = _vec(xt_resid, 2 * NR, "xt_resid", keep)
-    q.f_hat = _vec(f_hat, NR, "f_hat", keep)
-    q.xcos = _vec(xcos, NR, "xcos", keep)
-    q.IC_xt = _vec(IC_xt, 2 * NI, "IC_xt", keep)
-    q.IC_u1 = _vec(IC_u1, NI, "IC_u", keep)
-    q.IC_u2 = _vec(IC_u2, NI, "IC_u2", keep)
-    q.BC_xt = _vec(BC_xt, 2 * NB, "BC_xt", keep)
-    q.BC_u = _vec(BC_u, NB, "BC_u", keep)
-    a = _lib.TrainArgs()
-    a.epochs, a.lr, a.beta1, a.beta2, a.eps = int(epochs), float(lr), float(betas[0]), float(betas[1]), float(eps)
-    a.tol = float(tol) if tol is not None else -1.0
-    trace = grad = None
-    if trace_every and trace_every > 0 and epochs > 0:
-        trace = torch.zeros((epochs - 1) // trace_every + 1, dtype=torch.float32, device=dev)
-        a.trace_every, a.loss_trace_dev = int(trace_every), trace.data_ptr()
-    if want_grad:
-        grad = torch.zeros(n_params, dtype=torch.float32, device=dev)
-        a.grad_out_dev = grad.data_ptr()
-    status = torch.zeros(2, dtype=torch.float32, device=dev)
+    ptr = dict(xt_resid=_vec(xt_resid, 2 * NR, "xt_resid", keep), f_hat=_vec(f_hat, NR, "f_hat", keep),
+               xcos=_vec(xcos, NR, "xcos", keep), IC_xt=_vec(IC_xt, 2 * NI, "IC_xt", keep),
+               IC_u1=_vec(IC_u1, NI, "IC_u", keep), IC_u2=_vec(IC_u2, NI, "IC_u2", keep),
+               BC_xt=_vec(BC_xt, 2 * NB, "BC_xt", keep), BC_u=_vec(BC_u, NB, "BC_u", keep))
+    Q = (_lib.PinnProblem * nb)()
+    M = (_lib.Mlp * nb)()
+    A = (_lib.TrainArgs * nb)()
+    traces, grads = [None] * nb, [None] * nb
+    n_params = 0
+    for t in range(nb):
+        M[t], n_params = _mlp_of(models[t])
+        q = Q[t]
+        q.pde = PDE[pde]
+        pp = list(pde_params_list[t]) + [0.0, 0.0, 0.0]
+        q.p0, q.p1, q.p2 = float(pp[0]), float(pp[1]), float(pp[2])
+        q.NR, q.NI, q.NB = NR, NI, NB
+        for k, v in ptr.items():
+            setattr(q, k, v)
+        a = A[t]
+        a.epochs, a.lr, a.beta1, a.beta2, a.eps = int(epochs), float(lr), float(betas[0]), float(betas[1]), float(eps)
+        a.tol = float(tol) if tol is not None else -1.0
+        if trace_every and trace_every > 0 and epochs > 0:
+            traces[t] = torch.zeros((epochs - 1) // trace_every + 1, dtype=torch.float32, device=dev)
+            a.trace_every, a.loss_trace_dev = int(trace_every), traces[t].data_ptr()
+        if want_grad:
+            grads[t] = torch.zeros(n_params, dtype=torch.float32, device=dev)
+            a.grad_out_dev = grads[t].data_ptr()
+    status = torch.zeros((nb, 2), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         h = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device())
         stream = torch.cuda.current_stream(dev).cuda_stream
-        rc = _lib.lib().gptpinn_pinn_train(h, C.byref(q), C.byref(m), C.byref(a), status.data_ptr(), C.c_void_p(stream))
-    _lib.check(rc, "gptpinn_pinn_train")
-    out = dict(loss=status[0], status=status, trace=trace, grad=grad, n_params=n_params, _keep=keep)
-    return out
+        rc = _lib.lib().gptpinn_pinn_train_batch(h, nb, Q, M, A, status.data_ptr(), C.c_void_p(stream))
+    _lib.check(rc, "gptpinn_pinn_train_batch")
+    return [dict(loss=status[t, 0], status=status[t], trace=traces[t], grad=grads[t], n_params=n_params, _keep=keep)
+            for t in range(nb)]
+
+
+def train_fused(model, pde, pde_params, xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u, epochs, lr,
+                xcos=None, tol=None, trace_every=0, want_grad=False, betas=(0.9, 0.999), eps=1e-8):
+    """Train `model` (an nn.Module with `.linears`, updated in place).  Returns dict(loss, epochs[, trace, grad]).
+
+    loss = the last evaluated loss (the value the reference prints), as a 0-dim CUDA tensor (no sync here)."""
+    return train_fused_batch([model], pde, [pde_params], xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u, epochs, lr,
+                             xcos=xcos, tol=tol, trace_every=trace_every, want_grad=want_grad, betas=betas, eps=eps)[0]
 
 
 def epochs_done(result):

@@ -210,6 +210,13 @@ typedef struct {
 int  gptpinn_pinn_train(gptpinn_handle *h, const gptpinn_pinn_problem *prob, const gptpinn_mlp *net,
                         const gptpinn_train_args *args, float *status_dev, void *stream);
 
+/* `nbatch` (1..8) independent trainings in ONE launch -- the per-test-parameter loop of pinn_test / pinn_test_loss
+ * (KG_test.py:81-140, B_test.py:116-181).  probs[t] may differ only in the PDE parameters p0..p2, nets[t] only in
+ * the weight tensors, args[t] only in loss_trace_dev / grad_out_dev; everything else must be equal (checked).
+ * status_dev is [nbatch][2].  A training that meets `tol` stops stepping; the launch ends when all have.          */
+int  gptpinn_pinn_train_batch(gptpinn_handle *h, int nbatch, const gptpinn_pinn_problem *probs, const gptpinn_mlp *nets,
+                              const gptpinn_train_args *args, float *status_dev, void *stream);
+
 /* Host-only (no CUDA call): the work-item plan gptpinn_kg_sweep would build for this grid on a device
  * with n_sm SMs.  sl_hist[l] = number of items with 2^l sibling lanes; *covered = parameters assigned
  * (must equal Np).  Used by tests and for tuning; no reference counterpart.                            */

@@ -181,3 +181,61 @@ def test_dropin_pinn_test_sweeps_shapes_and_first_records():
     assert got.shape == (61, 1)
     assert abs(got[0, 0] - want0) <= 1e-5 * want0
     assert abs(got[1, 0] - want1000) <= 5e-2 * want1000        # 1000 Adam steps in fp32: trajectories agree to a few percent
+
+
+def test_batched_trainings_match_single_trainings():
+    """gptpinn_pinn_train_batch: several trainings in one launch = the same trainings one by one (the grid is cut into
+    equal CTA groups, so only the order of the gradient partial sums differs: 1e-4 on a 25-step trajectory); each training
+    keeps its own PDE parameters, trace and gradient; tolerance stops are per training."""
+    import B_data
+    import B_models
+    import KG_models
+    from gptpinn import pinn
+    make, params, t, xcos = _kg_setup(nc=21, ic=40, bc=40)
+    xt, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u = t
+    mus = [(-1.3, 0.4, 0.7), (-1.9, 0.1, 0.0), (-1.0, 1.0, 1.0), (-1.5, 0.5, 0.5), (-1.2, 0.9, 0.3)]
+
+    def fresh(mu):
+        net = KG_models.NN(np.array([2, 40, 40, 1]), *mu, xcos).cuda()
+        gg = torch.Generator().manual_seed(11)
+        for lin in net.linears:
+            lin.bias.data = (0.1 * torch.randn(lin.bias.shape, generator=gg)).cuda()
+        return net
+    singles, single_res = [], []
+    for mu in mus:
+        net = fresh(mu)
+        single_res.append(pinn.train_fused(net, "kg", mu, xt, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u, 25, 5e-4, xcos=xcos,
+                                           trace_every=1, want_grad=True))
+        singles.append(_pack_params(net).clone())
+    nets = [fresh(mu) for mu in mus]
+    res = pinn.train_fused_batch(nets, "kg", mus, xt, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u, 25, 5e-4, xcos=xcos,
+                                 trace_every=1, want_grad=True)
+    for k in range(len(mus)):
+        assert float((_pack_params(nets[k]) - singles[k]).abs().max() / singles[k].abs().max()) < 1e-4, k
+        assert float((res[k]["trace"] - single_res[k]["trace"]).abs().max() / single_res[k]["trace"].abs().max()) < 1e-4, k
+        assert float((res[k]["grad"] - single_res[k]["grad"]).abs().max() / single_res[k]["grad"].abs().max()) < 1e-3, k
+        assert pinn.epochs_done(res[k]) == 25
+    assert not torch.allclose(res[0]["trace"], res[1]["trace"])              # different PDE parameters, different runs
+    with pytest.raises(ValueError):
+        pinn.train_fused_batch([fresh(mus[0])] * 9, "kg", [mus[0]] * 9, xt, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u, 1, 5e-4, xcos=xcos)
+
+    # Burgers, per-training tolerance stop: trainings leave the launch at different epochs
+    bxt, bf, _ = B_data.residual_data(-1.0, 1.0, 0.0, 1.0, 19, 4)
+    bIC_xt, bIC_u, bBC_xt, bBC_u = B_data.ICBC_data(-1.0, 1.0, 0.0, 1.0, 21, 37)
+    bxt, bf, bIC_xt, bIC_u, bBC_xt, bBC_u = (x.cuda() for x in (bxt, bf, bIC_xt, bIC_u, bBC_xt, bBC_u))
+    nus = [0.9, 0.05, 0.37]
+    mk = lambda nu: B_models.NN(np.array([2, 20, 20, 20, 20, 1]), nu).cuda()
+    l0 = [float(pinn.train_fused(mk(nu), "burgers", (nu,), bxt, bf, bIC_xt, bIC_u, None, bBC_xt, bBC_u, 1, 0.0)["loss"]) for nu in nus]
+    tol = 0.6 * min(l0)
+    one = []
+    for nu in nus:
+        r = pinn.train_fused(mk(nu), "burgers", (nu,), bxt, bf, bIC_xt, bIC_u, None, bBC_xt, bBC_u, 300, 5e-3, tol=tol)
+        one.append((pinn.epochs_done(r), float(r["loss"])))
+    bnets = [mk(nu) for nu in nus]
+    rb = pinn.train_fused_batch(bnets, "burgers", [(nu,) for nu in nus], bxt, bf, bIC_xt, bIC_u, None, bBC_xt, bBC_u, 300, 5e-3, tol=tol)
+    done = [pinn.epochs_done(r) for r in rb]
+    assert len(set(done)) > 1                                                  # they do stop at different epochs
+    for k in range(len(nus)):
+        assert abs(done[k] - one[k][0]) <= 2, (done, one)                      # a loss within 1e-4 of tol may flip by one epoch
+        if done[k] < 300:
+            assert float(rb[k]["loss"]) < tol

@@ -26,6 +26,16 @@ def kg(epochs_fused=3000, epochs_torch=60):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     print(f"KG fused : {1e6 * dt / epochs_fused:9.1f} us/epoch  ({epochs_fused} epochs, loss {float(r['loss']):.4e})  -> 75000 epochs = {75000 * dt / epochs_fused:.1f} s")
+    for nb in (2, 3, 4, 6, 8):                 # several test parameters per launch (pinn_test): throughput per training
+        mus = [(-1.5 + 0.05 * k, 0.5, 0.5) for k in range(nb)]
+        nets = [KG_models.NN(np.array([2, 40, 40, 1]), *mu, xcos).cuda() for mu in mus]
+        pinn.train_fused_batch(nets, "kg", mus, xt, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u, 10, 5e-4, xcos=xcos)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pinn.train_fused_batch(nets, "kg", mus, xt, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u, epochs_fused // 2, 5e-4, xcos=xcos)
+        torch.cuda.synchronize()
+        dtb = time.perf_counter() - t0
+        print(f"KG fused, batch of {nb}: {1e6 * dtb / (epochs_fused // 2):9.1f} us/epoch per launch = {1e6 * dtb / (epochs_fused // 2) / nb:7.1f} us/epoch per training")
     net2 = KG_models.NN(np.array([2, 40, 40, 1]), -1.5, 0.5, 0.5, xcos).cuda()
     xr, ir = xt.clone().requires_grad_(), IC_xt.clone().requires_grad_()
     fn = lambda: net2.loss(xr, f_hat, ir, IC_u1, IC_u2, BC_xt, BC_u)
