@@ -113,7 +113,28 @@ def aux_measurements(device, d):
         e1.record()
         torch.cuda.synchronize()
         out["precompute_1e6_s"] = e0.elapsed_time(e1) * 1e-3
-    del bufs, xt
+    # config 5, second half: the GPT-PINN test sweep (KG_test.gpt_test: 200 test parameters from the default grid) on
+    # N_R = 10^6 residual rows, n = 15; a short run, fixed work per epoch
+    from gptpinn import sweep
+    g = torch.Generator(device=device).manual_seed(5)
+    for b_ in bufs:
+        b_.copy_(torch.randn(b_.shape, device=device, generator=g) * 0.3)
+    xcos6 = torch.randn((nc * nc, 1), device=device, generator=g) * 0.3
+    a_, b2_, g_ = np.linspace(-2, -1, 10), np.linspace(0, 1, 10), np.linspace(0, 1, 10)
+    kg_grid = np.array(np.meshgrid(a_, b2_, g_)).T.reshape(-1, 3)
+    test_mu = kg_grid[np.random.default_rng(1234).choice(1000, 200, replace=False)]
+    c0 = torch.full((N_NEURONS,), 1.0 / N_NEURONS, device=device)
+    dense = lambda ep: sweep.kg_sweep(test_mu, c0, bufs[0], bufs[1], bufs[2], d["out_IC"], d["out_IC_t"], d["out_BC"], xcos6,
+                                      torch.zeros_like(xcos6), d["IC_u1"], d["IC_u2"], d["BC_u"], ep, 0.001, want_c=False)
+    dense(2)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    dense(20)
+    e1.record()
+    torch.cuda.synchronize()
+    out["dense_1e6_test_sweep_param_epochs_per_s"] = 200 * 20 / (e0.elapsed_time(e1) * 1e-3)
+    del bufs, xt, xcos6
     net = KG_models.NN(np.array([2, 40, 40, 1]), -1.5, 0.5, 0.5, d["xcos"]).to(device)
     args = (net, "kg", (-1.5, 0.5, 0.5), d["xt_resid"], d["f_hat"], d["IC_xt"], d["IC_u1"], d["IC_u2"], d["BC_xt"], d["BC_u"])
     pinn.train_fused(*args, 10, 5e-4, xcos=d["xcos"])

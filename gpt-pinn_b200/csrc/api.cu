@@ -151,7 +151,7 @@ static double smsp_eff(double warps_per_smsp)
     if (warps_per_smsp <= 4.0) return 0.73 + 0.06 * (warps_per_smsp - 2.0);
     return 0.85;
 }
-static const double kL2BytesPerCycle = 2200.0;       // chip-wide L2 -> SM budget the planner allows itself
+static const double kL2BytesPerCycle = 4500.0;       // chip-wide L2 -> SM budget the planner allows itself
 
 // makespan of items handed out in list order (= ticket order) to `workers` identical workers, each item going to
 // the worker that frees up first.  Item times come in a few size classes, so worker loads are kept as a
