@@ -125,7 +125,7 @@ static double per_row_instr(int pde, int n, int M)
     const double fma = (pde == PDE_B ? 6.0 : 4.0) * n;
     return M * (fma + 8.0) + (pde == PDE_B ? 3.0 : 2.0) * ((n + 3) / 4) + 8.0;
 }
-static double item_instr(int pde, int n, int M, int SL, long long rows_total, long long tiles_pass, int rt, int K = 1)
+static double item_instr(int pde, int n, int M, int SL, long long rows_total, long long tiles_pass, int rt, int K = 1, bool shared_ring = false)
 {
     const int RL = 32 / SL;
     const long long tiles = (tiles_pass + K - 1) / K;                  // a team of K warps splits the tiles of a pass
@@ -135,7 +135,7 @@ static double item_instr(int pde, int n, int M, int SL, long long rows_total, lo
     // T: items with <= GP_REGT_MAX_SL sibling lanes form their T rows in registers (per row: extra loads + 2n FMA),
     // wider items build a per-warp T block in shared memory once per tile; plus ring bookkeeping per tile
     // per-tile ring cost in instruction-equivalents (mbarrier wait + first-row load latency, measured on B200)
-    const double ring = rt == RT_SHARED ? 300.0 : 150.0;
+    const double ring = shared_ring ? 300.0 : 200.0;
     const double build = SL <= GP_REGT_MAX_SL ? (double)tiles * ring + rows_lane * (2.0 * n + 6.0)
                                                : (double)tiles * (36.0 * (n / 4 + 1) * rt / 32.0 + ring);
     (void)rows_total;
@@ -283,7 +283,7 @@ static int make_plan(std::vector<ParamRow> &rows, int pde, int n, int n_sm, cons
         const int maxw = maxw_for_m(M);
         // ---- private rings: dynamic tickets, mixed item sizes ----
         if (mode != 1) {
-            const int wsmem = (int)((227.0 * 1024 - 96) / (NST_PRIV * slot_p + tblock_floats(pde, n, M, RT_PRIV) * 4 + NST_PRIV * 8 + TEAM_BYTES_PER_WARP));
+            const int wsmem = (int)((227.0 * 1024 - 96) / (NST_PRIV * slot_p + NST_PRIV * 8 + TEAM_BYTES_PER_WARP));
             const int maxw1 = std::max(1, std::min(maxw, wsmem));
           for (int K = 1; K <= 8; K <<= 1) {
             // teams of K warps share an item (finer time quanta for grids that give each warp only a few items)
@@ -332,7 +332,7 @@ static int make_plan(std::vector<ParamRow> &rows, int pde, int n, int n_sm, cons
                     const long long ctas = std::min<long long>(n_sm, (nit + W - 1) / W);
                     const long long full_rounds = nit / (ctas * W), rest = nit - full_rounds * ctas * W;
                     const double rounds = (double)(full_rounds + (rest > 0 ? 1 : 0));
-                    const double t_item = item_instr(pde, n, M, SL, 0, tiles_s, RT_SHARED);
+                    const double t_item = item_instr(pde, n, M, SL, 0, tiles_s, RT_SHARED, 1, true);
                     double issue = full_rounds * std::ceil(W / 4.0) * t_item / smsp_eff(W / 4.0);
                     if (rest > 0) {                                         // the last round runs with fewer warps per SM
                         const double wl = (double)((rest + ctas - 1) / ctas);
@@ -464,9 +464,9 @@ static int run_sweep(gptpinn_handle *h, int pde, int n, const Segments &seg, Pac
     p.counter = h->counter;
     p.K = plan.priv ? plan.K : 1;
 
-    const size_t tblk = (size_t)tblock_floats(pde, n, plan.M, RT) * 4;
+    const size_t tblk = (size_t)(n / 4 + 1) * 4 * RT * 4;                       // shared ring only: per-warp T block
     const size_t smem = plan.priv
-        ? (size_t)plan.W * NST_PRIV * slot * 4 + (size_t)plan.W * tblk + (((size_t)plan.W * NST_PRIV * sizeof(uint64_t) + 15) & ~(size_t)15)
+        ? (size_t)plan.W * NST_PRIV * slot * 4 + (((size_t)plan.W * NST_PRIV * sizeof(uint64_t) + 15) & ~(size_t)15)
               + (size_t)plan.W * TEAM_BYTES_PER_WARP
         : (size_t)NSTAGE * slot * 4 + (size_t)plan.W * tblk + 2 * NSTAGE * sizeof(uint64_t) + 16;
     if (smem > 227 * 1024) return fail(GPTPINN_E_UNSUPPORTED, "configuration needs %zu bytes of shared memory", smem);

@@ -22,30 +22,20 @@ namespace gp {
 // touch consecutive 16-B chunks (bank-conflict free), while lanes that share a row broadcast.
 // Rows past N and columns past n are zero, which contributes nothing to any sum.
 // ----------------------------------------------------------------------------------------
-// Two tile heights are compiled: RT = 32 for the "private ring" kernels (every warp streams its
-// own copy of the tiles: no inter-warp coupling, dynamic work distribution) and RT = 64 for the
-// "shared ring" kernels (all warps of a CTA consume one stream: small grids, rows split 32 ways).
-constexpr int RT_PRIV   = 32;
+// Both pipelines use 64-row tiles.  "Private ring" kernels: every warp (or team of warps) streams its own copy of the
+// tiles through a double buffer and builds T in place -- no inter-warp coupling, dynamic work distribution.
+// "Shared ring" kernels: all warps of a CTA consume one 4-deep stream (small grids, rows split 32 ways).
+constexpr int RT_PRIV   = 64;
 constexpr int RT_SHARED = 64;
 constexpr int NSTAGE   = 4;                  // shared ring depth
 constexpr int LOOKAHEAD = 2;                 // shared ring: tiles in flight ahead of the consumers
-constexpr int NST_PRIV = 3;                  // private ring depth (per warp)
+constexpr int NST_PRIV = 2;                  // private ring depth (per warp): one tile in use, one in flight
 constexpr int MAX_SEG  = 4;
 constexpr int RED_STRIDE = 20;               // floats per lane in the team-reduction buffer (16 used; 80-B stride: conflict-free LDS.128)
 constexpr int TEAM_BYTES_PER_WARP = 32 * RED_STRIDE * 4 + 4;     // reduction rows + the team's ticket slot
 
 constexpr int PDE_KG = 0, PDE_B = 1, PDE_AC = 2;
 
-#ifndef GP_PACKED_FWD
-#define GP_PACKED_FWD 0
-#endif
-// Experimental (off): kernels with M == 4 parameters per thread (Klein-Gordon, Allen-Cahn) run a packed FFMA2 forward
-// contraction; their per-warp T block holds interleaved (P, T) pairs and is twice the plain size.  Measured on B200
-// it is 8 % SLOWER than the scalar M = 4 kernel (three 64-bit operands always collide in the register file, and the
-// scalar backward FFMAs lose their operand reuse), so it stays disabled; see DESIGN.md "what did not work".
-// Host (shared-memory sizing) and device agree through these two functions.
-__host__ __device__ constexpr bool use_packed_fwd(int pde, int M) { return GP_PACKED_FWD && pde != PDE_B && M == 4; }
-__host__ __device__ constexpr int tblock_floats(int pde, int n, int M, int rt) { return (use_packed_fwd(pde, M) ? 2 : 1) * (n / 4 + 1) * 4 * rt; }
 
 template <int PDE> struct PdeTraits;
 template <> struct PdeTraits<PDE_KG> {      // residual: Ptt,Pxx,P | xcos,fhat ; IC: PIC,PICt | u1,u2 ; BC: PBC | BCu

@@ -55,31 +55,12 @@ __device__ __forceinline__ void load_row(const float *blk, int r, float (&v)[4 *
     for (int q = 0; q < NQX; ++q) load_quad<RT>(blk, r, q, v);
 }
 
-// Coefficient registers.  Plain kernels hold c as floats; the packed-forward kernels (use_packed_fwd) hold every c[k]
-// as the 64-bit pair (c[k], c[k]) so that one FFMA2 (fma.rn.f32x2) advances the P and the T contraction of a row
-// together: (u, t) += (P[k], T[k]) * (c[k], c[k]).  An FFMA2 reads three 64-bit register pairs in one dispatch slot,
-// where the two scalar FFMAs it replaces each pay a second register-file cycle for their third operand.
-template <bool PK> struct Coef { typedef float type; };
-template <> struct Coef<true> { typedef unsigned long long type; };
-__device__ __forceinline__ float cget(float v) { return v; }
-__device__ __forceinline__ float cget(unsigned long long v) { return __uint_as_float((unsigned)v); }
-__device__ __forceinline__ void cset(float &d, float v) { d = v; }
-__device__ __forceinline__ void cset(unsigned long long &d, float v) { asm("mov.b64 %0, {%1, %1};" : "=l"(d) : "f"(v)); }
-__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c)
-{
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ float lo32(unsigned long long v) { return __uint_as_float((unsigned)v); }
-__device__ __forceinline__ float hi32(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
-
-template <int N, typename CT>
-__device__ __forceinline__ float dotn(const float *a, const CT (&c)[N], float init)
+template <int N>
+__device__ __forceinline__ float dotn(const float *a, const float (&c)[N], float init)
 {
     float s = init;
 #pragma unroll
-    for (int k = 0; k < N; ++k) s = fmaf(a[k], cget(c[k]), s);
+    for (int k = 0; k < N; ++k) s = fmaf(a[k], c[k], s);
     return s;
 }
 
@@ -98,9 +79,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
     constexpr int NQ = (N + 3) / 4;          // column quads of a P block that hold data
     constexpr int NQT = N / 4 + 1;           // quads of T: N columns + the forcing column
     constexpr int SLOT = SlotFloats<PDE, RT>::value;
-    constexpr bool PK = use_packed_fwd(PDE, M);   // T block holds interleaved (P[k], T[k]) pairs, c is held as (c, c)
-    constexpr int TT = (PK ? 2 : 1) * NQT * QS;
-    typedef typename Coef<PK>::type creg;
+    constexpr int TT = NQT * QS;
     constexpr int VEC0 = TR::NARR * ARR, VEC1 = VEC0 + RT;
     constexpr int NST = PRIV ? NST_PRIV : NSTAGE;
     constexpr unsigned FULLM = 0xffffffffu;
@@ -108,13 +87,13 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // PRIV  : [W][NST][SLOT] rings | [W][TT] T blocks | full[W][NST]
+    // PRIV  : [W][NST][SLOT] rings | full[W][NST] | team buffers      (T is built in place over the staged tile)
     // shared: [NST][SLOT] ring     | [W][TT] T blocks | full[NST] empty[NST]
+    constexpr int TTW = PRIV ? 0 : TT;       // per-warp T block (shared ring only: the tile is shared, T is not)
     float *smem_f = reinterpret_cast<float *>(smem_raw);
     float *ring = PRIV ? smem_f + (size_t)warp * NST * SLOT : smem_f;
     float *Tall = smem_f + (size_t)(PRIV ? p.W : 1) * NST * SLOT;
-    float *Tw = Tall + warp * TT;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(Tall + p.W * TT);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(Tall + p.W * TTW);
     uint64_t *full = PRIV ? bars + warp * NST : bars;
     uint64_t *empty = bars + NST;            // shared mode only
     uint32_t *issued = reinterpret_cast<uint32_t *>(bars + (PRIV ? p.W * NST : 2 * NST));   // shared mode: tiles issued so far
@@ -220,8 +199,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
         const int SL = it.SL, RL = 32 / SL;
         const int sl = lane & (SL - 1), slice = lane / SL;
 
-        creg c[M][N];
-        float g[M][N];
+        float c[M][N], g[M][N];
         float sp0[M], sp1[M], mn[M];
 #pragma unroll
         for (int m = 0; m < M; ++m) {
@@ -235,7 +213,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
             }
 #pragma unroll
             for (int k = 0; k < N; ++k)
-                cset(c[m][k], valid ? (p.c0_per_param ? p.c0[(size_t)oi * N + k] : p.c0[k]) : 0.f);
+                c[m][k] = valid ? (p.c0_per_param ? p.c0[(size_t)oi * N + k] : p.c0[k]) : 0.f;
             mn[m] = __int_as_float(0x7f800000);
         }
 
@@ -326,6 +304,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                     }
                 } else if (active) {
                     // ---- per-warp T block (bit-identical to the reference's T tensor) -----
+                    // private ring: the staged tile belongs to this warp alone, so T overwrites the first matrix block
+                    // (P_tt / P_t: dead once T exists) element by element; shared ring: a block of its own
+                    float *Tw = PRIV ? const_cast<float *>(slot) : Tall + warp * TT;
 #pragma unroll
                     for (int e = lane; e < NQT * RT; e += 32) {     // NQT * RT / 32 independent entries: all loads issue before the first use
                         const int q = e / RT, r = e % RT;
@@ -354,15 +335,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                             }
                             set_comp(tv, N % 4, fc);
                         }
-                        if constexpr (PK) {      // interleave with the P quad: pair-quads 2q, 2q+1 = (P0,T0,P1,T1), (P2,T2,P3,T3)
-                            float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (q < NQ) pv = ld4(slot + 2 * ARR + o);
-                            if (q == N / 4) set_comp(pv, N % 4, 0.f);        // the forcing pair is (0, forcing): it seeds (u, t)
-                            st4(Tw + (2 * q) * QS + r * 4, make_float4(pv.x, tv.x, pv.y, tv.y));
-                            st4(Tw + (2 * q + 1) * QS + r * 4, make_float4(pv.z, tv.z, pv.w, tv.w));
-                        } else {
-                            st4(Tw + o, tv);
-                        }
+                        st4(Tw + o, tv);
                     }
                     __syncwarp();
 
@@ -371,51 +344,6 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                     int r = slice;
                     float fh = 0.f;
                     if (has_fhat) fh = slot[fhoff + r];
-                    if constexpr (PK) {
-                        unsigned long long PT[4 * NQT];         // pair k = (P[k], T[k]); pair N = (0, forcing)
-                        auto load_pairs = [&](int rr, int q2) {
-                            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(Tw + q2 * QS + rr * 4);
-                            PT[2 * q2] = v.x; PT[2 * q2 + 1] = v.y;
-                        };
-#pragma unroll
-                        for (int q2 = 0; q2 < 2 * NQT; ++q2) load_pairs(r, q2);
-                        for (; r < RT; r += RL) {
-                            const int rn = min(r + RL, RT - 1);
-                            float first[M], w2[M];
-                            unsigned long long acc[M];
-#pragma unroll
-                            for (int m = 0; m < M; ++m) acc[m] = PT[N];
-#pragma unroll
-                            for (int k = 0; k < N; ++k)
-#pragma unroll
-                                for (int m = 0; m < M; ++m) acc[m] = fma2(PT[k], c[m][k], acc[m]);
-#pragma unroll
-                            for (int m = 0; m < M; ++m) {
-                                const float u = lo32(acc[m]), tl = hi32(acc[m]);
-                                float d, nl;
-                                if constexpr (PDE == PDE_KG) { d = fmaf(sp0[m], u * u, tl); nl = sp1[m] * u; }
-                                else { const float u2 = u * u; d = fmaf(sp0[m], u2 * u, tl); nl = sp1[m] * u2; }
-                                lacc[m] = fmaf(d, d, lacc[m]);
-                                first[m] = has_fhat ? d + fh : d;
-                                w2[m] = first[m] * nl;
-                            }
-                            if (has_fhat) fh = slot[fhoff + rn];
-#pragma unroll
-                            for (int q = 0; q < NQT; ++q) {
-#pragma unroll
-                                for (int m = 0; m < M; ++m)
-#pragma unroll
-                                    for (int kk = 0; kk < 4; ++kk) {
-                                        const int k = 4 * q + kk;
-                                        if (k < N) {
-                                            g[m][k] = fmaf(first[m], hi32(PT[k]), g[m][k]);
-                                            g[m][k] = fmaf(w2[m], lo32(PT[k]), g[m][k]);
-                                        }
-                                    }
-                                load_pairs(rn, 2 * q); load_pairs(rn, 2 * q + 1);
-                            }
-                        }
-                    } else {
                     float Tv[4 * NQT], Pv[4 * NQ];
                     load_row<NQT, RT>(Tw, r, Tv);
                     load_row<NQ, RT>(Pblk, r, Pv);
@@ -497,7 +425,6 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                             }
                         }
                     }
-                    }   // !PK
                 }
                 release();
             }
@@ -650,14 +577,14 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                         p.m_out[oi] = mn[m];
                         if (p.c_out != nullptr) {
 #pragma unroll
-                            for (int k = 0; k < N; ++k) p.c_out[(size_t)oi * N + k] = cget(c[m][k]);
+                            for (int k = 0; k < N; ++k) p.c_out[(size_t)oi * N + k] = c[m][k];
                         }
                     }
                 }
                 if (!last) {
                     if (loss < mn[m]) mn[m] = loss;
 #pragma unroll
-                    for (int k = 0; k < N; ++k) cset(c[m][k], __fsub_rn(cget(c[m][k]), __fmul_rn(p.lr, g[m][k])));
+                    for (int k = 0; k < N; ++k) c[m][k] = __fsub_rn(c[m][k], __fmul_rn(p.lr, g[m][k]));
                 }
             }
         }   // epochs
