@@ -9,15 +9,18 @@
 //           T (KG: same (alpha,beta); their gammas differ).  Lanes = SL sibling-lanes x RL
 //           row-slices (SL*RL = 32); each thread owns M parameters: c[M][N], grad[M][N] and
 //           the loss sums live in registers for the whole run.
-//   tiles = the packed activation stream (common.cuh) enters shared memory by TMA bulk copies
-//           (cp.async.bulk + mbarrier complete_tx).  Two pipeline flavours:
-//             PRIV = true : every warp owns a 3-deep ring of 32-row tiles and pulls work items
-//                           from a global ticket -- no inter-warp coupling at all (large grids);
-//             PRIV = false: the W warps of a CTA share a 4-deep ring of 64-row tiles with
-//                           full/empty mbarriers and static rounds (small grids, RL = 32).
-//   T     = per-warp [NQT][RT][4] block in shared memory, rebuilt from the staged P-derivative
-//           tiles for every residual tile (2 FMA/element amortised over the siblings) so the
-//           inner loop spends the reference's 4n FMA per row and parameter.
+//   tiles = the packed activation stream (common.cuh: 64-row tiles) enters shared memory by TMA bulk
+//           copies (cp.async.bulk + mbarrier complete_tx).  Two pipeline flavours:
+//             PRIV = true : every warp owns a double buffer of tiles and pulls work items from a
+//                           global ticket -- no inter-warp coupling (large grids).  K warps may team
+//                           up on one item: they split the tiles of a pass K ways and sum their
+//                           gradients through shared memory once per epoch (few items per warp);
+//             PRIV = false: the W warps of a CTA share a 4-deep ring with full/empty mbarriers and
+//                           static rounds (small grids, RL = 32).
+//   T     = per-warp [NQT][RT][4] block, rebuilt from the staged P-derivative tiles for every
+//           residual tile (2 FMA/element amortised over the siblings) so the inner loop spends the
+//           reference's 4n FMA per row and parameter.  PRIV builds it in place over the tile's first
+//           matrix block (the tile copy is the warp's own); the shared ring keeps a block per warp.
 //   epoch = one pass over the tile stream (all residual, IC, BC tiles); at its end the RL
 //           row-slices are summed with xor-shuffles (fixed order => bitwise deterministic),
 //           the loss of the *current* c falls out of the same pass, then c <- c - lr*grad.
