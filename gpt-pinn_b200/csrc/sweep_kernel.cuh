@@ -235,7 +235,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
             int gbase = 0;                          // pass-relative index of the segment's first tile
             for (int t = (tw - gbase) & (K - 1); t < p.ntile[0]; t += K) {
                 const float *slot = acquire();
-                if (active && SL <= REGT_MAX_SL) {
+                if (active && (SL <= REGT_MAX_SL || has_fhat)) {
+                    // ---- (also the general path for a non-zero f_hat target -- never the case in the reference's problems --
+                    //      which keeps the f_hat handling out of the fast loops below)
                     // ---- few sibling lanes: a T row is used by at most REGT_MAX_SL lanes, so staging the whole T block
                     //      through shared memory costs more than it saves.  Each lane forms the T quads of its own row in
                     //      registers (fused multiply-adds: within one ulp of the reference's separately rounded T).
@@ -330,12 +332,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                         }
                         if (q == N / 4) {       // forcing column: (xcos) - fhat, multiplied by an implicit c = 1
                             float fc = 0.f;
-                            if constexpr (PDE == PDE_KG) {
-                                fc = slot[VEC0 + r];
-                                if (has_fhat) fc = __fsub_rn(fc, slot[VEC1 + r]);
-                            } else {
-                                if (has_fhat) fc = -slot[VEC0 + r];
-                            }
+                            if constexpr (PDE == PDE_KG) fc = slot[VEC0 + r];          // f_hat == 0 on this path
                             set_comp(tv, N % 4, fc);
                         }
                         st4(Tw + o, tv);
@@ -343,10 +340,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                     __syncwarp();
 
                     const float *Pblk = slot + (PDE == PDE_B ? 3 : 2) * ARR;
-                    const int fhoff = (PDE == PDE_KG) ? VEC1 : VEC0;
                     int r = slice;
-                    float fh = 0.f;
-                    if (has_fhat) fh = slot[fhoff + r];
                     float Tv[4 * NQT], Pv[4 * NQ];
                     load_row<NQT, RT>(Tw, r, Tv);
                     load_row<NQ, RT>(Pblk, r, Pv);
@@ -364,10 +358,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                                 const float t1 = dotn<N>(Tv, c[m], Tv[N]);
                                 const float d = fmaf(u, ux, t1);
                                 lacc[m] = fmaf(d, d, lacc[m]);
-                                first[m] = has_fhat ? d + fh : d;
+                                first[m] = d;
                                 wx[m] = first[m] * u; wp[m] = first[m] * ux;
                             }
-                            if (has_fhat) fh = slot[fhoff + rn];
 #pragma unroll
                             for (int q = 0; q < NQT; ++q) {
 #pragma unroll
@@ -404,10 +397,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                                 if constexpr (PDE == PDE_KG) { d = dotn<N>(Tv, c[m], fmaf(sp0[m], u * u, Tv[N])); nl = sp1[m] * u; }            // g*u^2 ; 2g*u
                                 else { const float u2 = u * u; d = dotn<N>(Tv, c[m], fmaf(sp0[m], u2 * u, Tv[N])); nl = sp1[m] * u2; }         // e*u^3 ; 3e*u^2
                                 lacc[m] = fmaf(d, d, lacc[m]);
-                                first[m] = has_fhat ? d + fh : d;          // the update ignores fhat (N3)
+                                first[m] = d;
                                 w2[m] = first[m] * nl;
                             }
-                            if (has_fhat) fh = slot[fhoff + rn];
 #if GP_PHASE_SYNC
                             __syncwarp();          // scheduling fence: keeps the forward contractions of all M parameters together
 #endif
