@@ -235,6 +235,18 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
+    # stdout carries exactly ONE JSON line: anything libraries print meanwhile (e.g. NCCL's version banner at communicator
+    # creation) is sent to stderr; the real stdout is restored for the result line only
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -266,14 +278,14 @@ def main():
         total = time.perf_counter() - t0
         value = done / total
         sample = f"{n_params} params x {ep} epochs per step (update + loss, no early exit), torch CPU, {threads} threads"
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": "param_epochs_per_sec", "value": value, "unit": "param*epochs/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "sampled": sample},
             "cpu_baseline": {"value": value, "unit": "param*epochs/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "param*epochs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}))
+            "gpu_launches": 0})
         return
 
     # ------------------------------------------------------------------ B200 arm
@@ -428,7 +440,7 @@ def main():
         "clocks": clocks, "precompute_s": {"value": precompute_s, "what": f"one neuron, all KG point sets (N_R={N}), CUDA closed-form kernel"},
         "wall_s_timed_region": t_wall, "ffma_peak_tflops_measured": ffma_peak, "aux": aux,
     }
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
