@@ -281,6 +281,16 @@ static int make_plan(std::vector<ParamRow> &rows, int pde, int n, int n_sm, cons
         if (a->cfg_M > 0 && M != a->cfg_M) continue;
         if (a->cfg_M == 0 && M > Mcap) continue;
         const int maxw = maxw_for_m(M);
+        if (a->cfg_M == 0 && best < 1e300) {
+            // lower bound for this M: every sibling lane at the per-lane cost of the widest item, perfectly spread over all
+            // warps an SM can hold -- if even that loses to the best plan so far, skip the search
+            double lanes = 0.0;
+            for (int g = 0; g < plan.groups; ++g) lanes += (double)((gstart[g + 1] - gstart[g] + M - 1) / M);
+            const double per_lane = std::min(item_instr(pde, n, M, 32, 0, tiles_p, RT_PRIV) / 32.0, item_instr(pde, n, M, 32, 0, tiles_s, RT_SHARED, 1, true) / 32.0);
+            const double wps = maxw / 4.0;
+            const double lb = lanes * per_lane / ((double)n_sm * maxw) * std::ceil(wps) / smsp_eff(wps);
+            if (lb >= best) continue;
+        }
         // ---- private rings: dynamic tickets, mixed item sizes ----
         if (mode != 1) {
             const int wsmem = (int)((227.0 * 1024 - 96) / (NST_PRIV * slot_p + NST_PRIV * 8 + TEAM_BYTES_PER_WARP));
