@@ -30,6 +30,10 @@
 
 namespace cg = cooperative_groups;
 
+#ifndef GP_PINN_UNROLL
+#define GP_PINN_UNROLL 1
+#endif
+
 namespace gp {
 
 constexpr int CH = 5;                 // v, x, t, q, r
@@ -91,6 +95,7 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
     constexpr int NS = CH * PT + 1;                          // neuron stride of a staging buffer (odd: conflict-free column reads)
     constexpr int STG = WMAX * NS;                           // one staging buffer [neuron][channel][point]
     constexpr int NHH = NH > 1 ? NH - 1 : 1;
+    constexpr int UNR = GP_PINN_UNROLL;                      // rows of a layer GEMM in flight together
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) float smem[];
     const int P = d.n_params;
@@ -191,8 +196,10 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
 #pragma unroll
                         for (int c = 1; c < CH; ++c) z[l + 1][c][jj] = 0.f;
                     }
-                    const int wi = d.layers[l + 1];
-                    for (int i = 0; i < wi; ++i) {
+                    // all WMAX rows: rows past the layer width are zero in A and in wt (compile-time trip count: the loads
+                    // of the next rows are issued under the FMAs of the current ones)
+#pragma unroll UNR
+                    for (int i = 0; i < WMAX; ++i) {
                         float av[CH], wv[GJP];
 #pragma unroll
                         for (int c = 0; c < CH; ++c) av[c] = A_s[i * NS + c * PT + lane];
@@ -357,8 +364,8 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
                     for (int jj = 0; jj < GJ; ++jj)
 #pragma unroll
                         for (int c = 0; c < CH; ++c) ab[c][jj] = 0.f;
-                    const int wo = d.layers[l + 1];
-                    for (int j = 0; j < wo; ++j) {
+#pragma unroll UNR
+                    for (int j = 0; j < WMAX; ++j) {             // rows past the layer width are zero in B and in wp
                         float zv[CH], wv[GJP];
 #pragma unroll
                         for (int c = 0; c < CH; ++c) zv[c] = B_s[j * NS + c * PT + lane];
