@@ -41,7 +41,7 @@ constexpr int NG = 4;                 // neuron groups = warps per block
 constexpr int PT = 32;                // points per tile = lanes
 constexpr int TJG = 4, TIG = 8;       // lane tiling of a weight-gradient matrix: 4 output groups x 8 input groups
 
-__device__ __forceinline__ void act_derivs(int act, float z, float &s0, float &s1, float &s2, float &s3)
+__device__ __noinline__ void act_derivs(int act, float z, float &s0, float &s1, float &s2, float &s3)
 {
     if (act == 0) {                   // cos
         float sn, cs;
