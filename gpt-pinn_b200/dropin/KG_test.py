@@ -14,7 +14,7 @@ from KG_models import NN
 from _common import offline, pinn, sweep
 
 device = torch.device("cuda")
-PINN_BATCH = 8          # test parameters per training launch (1..8): 38 us per Adam epoch and training at the KG sizes, 80 us alone
+PINN_BATCH = 8          # test parameters per training launch (1..8): 31 us per Adam epoch and training at the KG sizes, 66 us alone
 
 
 def gpt_test(kg_test, out, out_xx, out_tt, out_IC, out_IC_t, out_BC, fhat,
