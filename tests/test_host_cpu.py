@@ -215,3 +215,22 @@ def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert "workload" in d["config"]
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"])
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_batched_trainer_rejects_bad_batches_without_a_gpu():
+    """Host-side checks of train_fused_batch: batch size limits, one parameter tuple per model, no CPU fallback."""
+    import KG_models
+    from gptpinn import _lib, pinn
+    xcos = torch.zeros(4, 1)
+    nets = [KG_models.NN(np.array([2, 40, 40, 1]), -1.5, 0.5, 0.5, xcos) for _ in range(2)]
+    xt = torch.zeros(4, 2)
+    one = torch.zeros(4, 1)
+    args = (xt, one, xt, one, one, xt, one, 1, 5e-4)
+    with pytest.raises(ValueError):
+        pinn.train_fused_batch(nets, "kg", [(-1.5, 0.5, 0.5)], *args, xcos=xcos)              # 2 models, 1 parameter tuple
+    with pytest.raises(ValueError):
+        pinn.train_fused_batch([], "kg", [], *args, xcos=xcos)
+    with pytest.raises(ValueError):
+        pinn.train_fused_batch(nets * 5, "kg", [(-1.5, 0.5, 0.5)] * 10, *args, xcos=xcos)     # more than MAX_BATCH
+    with pytest.raises(_lib.GptPinnError):
+        pinn.train_fused_batch(nets, "kg", [(-1.5, 0.5, 0.5)] * 2, *args, xcos=xcos)          # CPU tensors: no fallback
