@@ -18,6 +18,9 @@
  *     the reference) are contiguous.
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls enqueue
  *     work and return; they synchronise only where stated.
+ *   - a handle owns one workspace (packed tile stream, work-item tables, trainer state): calls on the same handle
+ *     must be issued from one host thread at a time and on one stream (or on streams the caller orders); use one
+ *     handle per stream / per device for concurrent work.  The handle belongs to the device current at creation.
  *   - every function returns GPTPINN_OK (0) or a negative GPTPINN_E_* code and never throws;
  *     gptpinn_last_error() gives the message of the last failure on the calling thread.
  *   - scalars that the reference multiplies into fp32 tensors (alpha, beta, gamma, 2*gamma,
