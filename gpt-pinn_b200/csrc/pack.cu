@@ -38,15 +38,60 @@ cudaError_t launch_pack(const PackJobs &jobs, float *stream, long long max_rows,
 }
 
 // ---- exact arg-max scan ---------------------------------------------------
-// Sequential semantics, parallel filter: L only grows, so a 1024-entry chunk in which no entry
+// Sequential semantics: L = 0, idx = -1; for p in grid order: if !(m_p < L) && f_p > L: L = f_p, idx = p.
+//
+// Fast path (parallel).  Let w be the FIRST index of F = max f (NaN never wins) and X = max(0, max_{p<w} f_p).
+// Every earlier f_p is strictly below F and the running maximum when the scan reaches w is at most X, so
+// !(m_w < X) implies that w is accepted there, and nothing after w can exceed F: the answer is (F, w).  If all
+// f_p <= 0 nothing is ever accepted: (0, -1).  Only when m_w < X (a winner whose loss once dipped below an earlier
+// final loss) the answer depends on the order of acceptance, and the block falls back to the sequential scan.
+//
+// Fallback (sequential semantics, parallel filter): L only grows, so a 1024-entry chunk in which no entry
 // satisfies  !(m < L) && f > L  for the L at chunk entry cannot change L and is skipped.
+__device__ __forceinline__ void best_of(float &bf, int &bi, float of, int oi)
+{
+    if (of > bf || (of == bf && oi < bi)) { bf = of; bi = oi; }
+}
+
 __global__ void argmax_scan_kernel(const float *__restrict__ f, const float *__restrict__ m, int Np,
                                    float *L_out, int *idx_out)
 {
-    __shared__ float sL;
-    __shared__ int sIdx;
-    if (threadIdx.x == 0) { sL = 0.f; sIdx = -1; }
+    __shared__ float sL, sF[32], sX[32];
+    __shared__ int sIdx, sI[32], sW, sDone;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const float NEG = __int_as_float(0xff800000);
+    // ---- fast path, step 1: first arg-max of f
+    float bf = NEG; int bi = 0x7fffffff;
+    for (int p = threadIdx.x; p < Np; p += blockDim.x) { const float v = f[p]; if (v > bf) { bf = v; bi = p; } }
+    for (int off = 16; off; off >>= 1) best_of(bf, bi, __shfl_xor_sync(0xffffffffu, bf, off), __shfl_xor_sync(0xffffffffu, bi, off));
+    if (lane == 0) { sF[warp] = bf; sI[warp] = bi; }
     __syncthreads();
+    if (warp == 0) {
+        bf = lane < nwarp ? sF[lane] : NEG; bi = lane < nwarp ? sI[lane] : 0x7fffffff;
+        for (int off = 16; off; off >>= 1) best_of(bf, bi, __shfl_xor_sync(0xffffffffu, bf, off), __shfl_xor_sync(0xffffffffu, bi, off));
+        if (lane == 0) { sF[0] = bf; sW = bi; }
+    }
+    __syncthreads();
+    const float F = sF[0];
+    const int w = sW;
+    // ---- step 2: X = max(0, max_{p < w} f_p)
+    float bx = 0.f;
+    if (F > 0.f)
+        for (int p = threadIdx.x; p < w; p += blockDim.x) { const float v = f[p]; if (v > bx) bx = v; }
+    for (int off = 16; off; off >>= 1) bx = fmaxf(bx, __shfl_xor_sync(0xffffffffu, bx, off));
+    if (lane == 0) sX[warp] = bx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float X = 0.f;
+        for (int k = 0; k < nwarp; ++k) X = fmaxf(X, sX[k]);
+        sDone = 0;
+        if (!(F > 0.f)) { *L_out = 0.f; *idx_out = -1; sDone = 1; }
+        else if (!(m[w] < X)) { *L_out = F; *idx_out = w; sDone = 1; }
+        sL = 0.f; sIdx = -1;
+    }
+    __syncthreads();
+    if (sDone) return;
+    // ---- fallback: the literal scan with a parallel chunk filter
     for (int base = 0; base < Np; base += blockDim.x) {
         const int p = base + threadIdx.x;
         const float L = sL;

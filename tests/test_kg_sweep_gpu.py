@@ -146,6 +146,22 @@ def test_argmax_scan_matches_oracle_on_random_and_ties():
         L, idx = sweep.argmax_scan(torch.from_numpy(f).cuda(), torch.from_numpy(m).cuda())
         Lo, io = oracle.argmax_scan(f, m)
         assert idx == io and float(L) == Lo, Np
+    # small adversarial cases from a discrete value set: ties at the maximum, non-positive losses, NaN in f and m,
+    # winners whose minimum dipped below an earlier final loss (the order-dependent fallback), nothing accepted
+    vals = np.array([-1.0, 0.0, 0.25, 0.5, 0.75, 1.0, np.nan], np.float32)
+    for trial in range(300):
+        Np = int(rng.integers(1, 48))
+        f = vals[rng.integers(0, len(vals), Np)]
+        m = vals[rng.integers(0, len(vals), Np)]
+        L, idx = sweep.argmax_scan(torch.from_numpy(f).cuda(), torch.from_numpy(m).cuda())
+        Lo, io = oracle.argmax_scan(f, m)
+        assert idx == io and float(L) == Lo, (trial, f, m)
+    big = np.full(5000, 0.5, np.float32); mb = big.copy()
+    big[4000] = 0.9; mb[4000] = 0.1; big[10] = 0.6                          # the arg-max is NOT accepted (m_w < 0.6): fallback
+    L, idx = sweep.argmax_scan(torch.from_numpy(big).cuda(), torch.from_numpy(mb).cuda())
+    assert (float(L), idx) == oracle.argmax_scan(big, mb)
+    neg = -np.ones(3000, np.float32)
+    assert sweep.argmax_scan(torch.from_numpy(neg).cuda(), torch.from_numpy(neg).cuda())[1] == -1
 
 
 def test_kg_dense_rows_config5_properties():
