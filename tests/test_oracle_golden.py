@@ -194,3 +194,56 @@ def test_torch_port_matches_reference():
     assert float(L) == float(g["n7_L"]) and np.array_equal(g["grid"][idx], g["n7_case"])
     c, loss = torch_port.kg_trajectory(g["grid"][5], c0, mats, int(g["epochs"]), lr_of(g, 2))
     assert np.array_equal(c.numpy(), g["n7_c"][5]) and float(loss) == float(g["n7_f"][5])
+
+
+def _update_vs_numeric_gradient(kind, prob, mu, c0, lr=0.01, h=4e-3):
+    """(c - update(c)) / lr from one epoch of the oracle vs central differences of the oracle's loss (f64 build)."""
+    n = c0.size
+    grid = np.asarray([mu], np.float64).reshape(1, -1)
+    one = oracle.sweep(kind, prob, grid, c0, 1, lr, 0, "f64")
+    g_update = (c0.astype(np.float64) - one["c"][0].astype(np.float64)) / lr
+    g_num = np.zeros(n)
+    for k in range(n):
+        e = np.zeros(n, np.float32); e[k] = h
+        lp = oracle.sweep(kind, prob, grid, c0 + e, 0, lr, 0, "f64")["f"][0]
+        lm = oracle.sweep(kind, prob, grid, c0 - e, 0, lr, 0, "f64")["f"][0]
+        g_num[k] = (float(lp) - float(lm)) / (float((c0 + e)[k]) - float((c0 - e)[k]))
+    return g_update, g_num
+
+
+def test_update_is_the_loss_gradient_only_for_the_shipped_targets():
+    """SURVEY N3 as a property test: with the reference's shipped targets (f_hat = 0, IC_u2 = 0, Burgers BC_u = 0) the
+    hand-derived update direction equals the gradient of the loss; with a non-zero IC_u2 (KG) or BC_u (Burgers) it does
+    not, because the update ignores those targets while the loss does not -- the oracle implements the update as written."""
+    rng = np.random.default_rng(5)
+    g = load_golden("kg_small")
+    n = 7
+    c0 = (np.full(n, 1.0 / n) + 0.05 * rng.standard_normal(n)).astype(np.float32)
+    gu, gn = _update_vs_numeric_gradient("kg", _kg_prob(g, n), g["grid"][17], c0)
+    assert np.max(np.abs(gu - gn)) < 2e-3 * np.max(np.abs(gn)), (gu, gn)
+    g2 = dict(g)
+    g2["IC_u2"] = (2000.0 * g["out_IC_t"][:, 0:1]).astype(np.float32)         # correlated with a (small) P_IC_t column
+    gu2, gn2 = _update_vs_numeric_gradient("kg", _kg_prob(g2, n), g["grid"][17], c0)
+    assert np.max(np.abs(gu2 - gu)) < 1e-6 * np.max(np.abs(gu))           # the update does not see IC_u2 ...
+    assert np.max(np.abs(gu2 - gn2)) > 2e-2 * np.max(np.abs(gn2))         # ... the loss does
+
+    b = load_golden("b_small")
+    nb = int(b["ns"][-1])
+    c0b = b[f"n{nb}_c0"][3].astype(np.float32) + (0.02 * rng.standard_normal(nb)).astype(np.float32)
+    b0 = dict(b)
+    b0["BC_u"] = np.zeros_like(b["BC_u"]); b0["f_hat"] = np.zeros_like(b["f_hat"])
+    gub, gnb = _update_vs_numeric_gradient("b", _b_prob(b0, nb), [b["grid"][3]], c0b)
+    assert np.max(np.abs(gub - gnb)) < 2e-3 * np.max(np.abs(gnb)), (gub, gnb)
+    b1 = dict(b0)
+    b1["BC_u"] = (2.0 * b["out_BC"][:, 0:1] + 0.5).astype(np.float32)
+    gub1, gnb1 = _update_vs_numeric_gradient("b", _b_prob(b1, nb), [b["grid"][3]], c0b)
+    assert np.max(np.abs(gub1 - gub)) < 1e-6 * np.max(np.abs(gub))
+    assert np.max(np.abs(gub1 - gnb1)) > 2e-2 * np.max(np.abs(gnb1))
+
+    a = load_golden("ac_small")
+    na = int(a["ns"][-1])
+    c0a = (np.full(na, 1.0 / na) + 0.05 * rng.standard_normal(na)).astype(np.float32)
+    a0 = dict(a)
+    a0["f_hat"] = np.zeros_like(a["f_hat"])
+    gua, gna = _update_vs_numeric_gradient("ac", _ac_prob(a0, na), a["grid"][5], c0a, lr=0.0025)
+    assert np.max(np.abs(gua - gna)) < 2e-3 * np.max(np.abs(gna)), (gua, gna)
