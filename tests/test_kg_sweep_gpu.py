@@ -240,3 +240,30 @@ def test_kg_config4_grid_properties():
     assert rel_scalar(f[pick], o["f"]) < TOL
     assert rel_scalar(m[pick], o["m"]) < TOL
     assert rel_vec(c[pick], o["c"]) < TOL
+
+
+def test_kg_diverging_parameters_nan_semantics():
+    """A learning rate at which part of the grid diverges (parity case 2): 16 of 60 parameters end in NaN, 4 in
+    losses of 1e9..1e23, the rest converge.  The CUDA path must produce NaN for the same parameters, agree on the finite
+    ones, and select what the reference's literal loop selects (a NaN loss never breaks and never wins)."""
+    from gptpinn import sweep
+    from oracle import oracle
+    g = load_golden("kg_small")
+    d = _dev(g, KG_NAMES)
+    n, epochs, lr = 7, 60, 0.14
+    pr = oracle.kg_problem(n, *(g[k] for k in KG_NAMES))
+    c0 = np.full(n, 1.0 / n, np.float32)
+    o = oracle.sweep("kg", pr, g["grid"], c0, epochs, lr, 0, "f64")
+    Lo, io = oracle.kg_offline_literal(pr, g["grid"], c0, epochs, lr, "f64")
+    assert np.isnan(o["f"]).sum() >= 8 and np.isfinite(o["f"]).sum() >= 8          # the case is what it claims to be
+    for cfg in (None, dict(mode=1), dict(mode=2, K=1)):
+        r = _run(d, n, g["grid"], epochs, lr, cfg=cfg)
+        f, m = r["f"].cpu().numpy(), r["m"].cpu().numpy()
+        assert np.array_equal(np.isnan(f), np.isnan(o["f"])), cfg
+        fin = np.isfinite(o["f"])
+        assert np.max(np.abs(f[fin] - o["f"][fin]) / np.abs(o["f"][fin])) < 1e-4, cfg   # diverging-but-finite losses amplify rounding
+        small = fin & (o["f"] < 10)
+        assert rel_scalar(f[small], o["f"][small]) < TOL, cfg
+        L, idx = sweep.argmax_scan(r["f"], r["m"])
+        assert idx == io and abs(float(L) - Lo) <= 1e-4 * abs(Lo), cfg
+        assert (float(L), idx) == oracle.argmax_scan(f, m)
