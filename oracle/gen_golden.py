@@ -234,8 +234,17 @@ def trajectories(make_pair, grid, c0_of, n, epochs, rec_every):
 # Burgers
 # --------------------------------------------------------------------------------------
 def gen_b_small():
+    _gen_burgers("b_small", 24, 10, 40, 40, [1, 2, 5, 9], np.delete(np.linspace(0.005, 1, 33), [16]), 300, 50, True)
+
+
+def gen_b_full():
+    """Reference default sizes (B_main.py:34-37: N_R = 10 000, N_IC = 200, N_BC = 400), n = 9, 2000 epochs, 6 parameters."""
+    _gen_burgers("b_full", 100, 10, 200, 200, [9], np.linspace(0.005, 1, 129)[[3, 30, 57, 77, 101, 126]], 2000, 500, False)
+
+
+def _gen_burgers(tag, Nc, N_test, BC_pts, IC_pts, ns, grid, epochs, rec, small):
     m = _import_ref("Burgers", ["B_data", "B_models", "B_precomp", "B_optimizer", "B_train", "B_test"])
-    Nc, N_test, BC_pts, IC_pts, nmax = 24, 10, 40, 40, 9
+    nmax = 9
     xt_resid, f_hat, xt_test = m["B_data"].residual_data(-1.0, 1.0, 0.0, 1.0, Nc, N_test)
     IC_xt, IC_u, BC_xt, BC_u = m["B_data"].ICBC_data(-1.0, 1.0, 0.0, 1.0, BC_pts, IC_pts)
     xt_resid = xt_resid.requires_grad_()
@@ -250,8 +259,9 @@ def gen_b_small():
     for i in range(nmax):
         pinn = m["B_models"].NN(layers, neurons[i])
         _randomize(pinn, 2000 + i, scale=1.0, pert=0.05)
-        for k, a in _weights(pinn).items():
-            save[f"pinn{i}_{k}"] = a
+        if small:
+            for k, a in _weights(pinn).items():
+                save[f"pinn{i}_{k}"] = a
         m["B_precomp"].inputs(pinn, xt_resid, out, out_t, out_x, out_xx, out_IC, out_BC, IC_xt, BC_xt, i,
                               out_test, xt_test, N, num_mag, idx_list)
     bufs = dict(out=out, out_t=out_t, out_x=out_x, out_xx=out_xx, out_IC=out_IC, out_BC=out_BC, out_test=out_test)
@@ -259,8 +269,7 @@ def gen_b_small():
     save.update({k: v.numpy() for k, v in bufs.items()})
     save.update(xt_resid=xt_resid.detach().numpy(), xt_test=xt_test.numpy(), IC_xt=IC_xt.numpy(), BC_xt=BC_xt.numpy(),
                 IC_u=IC_u.numpy(), BC_u=BC_u.numpy(), f_hat=f_hat.numpy(), idx_list=idx_list.numpy(), neurons=neurons)
-    grid = np.delete(np.linspace(0.005, 1, 33), [16])
-    ns, epochs, lr, rec = [1, 2, 5, 9], 300, 0.02, 50
+    lr = 0.02
     save.update(grid=grid, ns=np.array(ns), epochs=epochs, lr=lr, rec_every=rec)
     for n in ns:
         v = {k: bufs[k][:, :n] for k in ("out", "out_t", "out_x", "out_xx", "out_IC", "out_BC")}
@@ -289,7 +298,13 @@ def gen_b_small():
         save[f"n{n}_c"], save[f"n{n}_f"], save[f"n{n}_m"], save[f"n{n}_trace"] = C, F, M, T
         save[f"n{n}_L"] = np.float32(float(L))
         save[f"n{n}_case"] = np.float64(case)
-        print("b_small n", n, "L", float(L), "case", case, flush=True)
+        print(tag, "n", n, "L", float(L), "case", case, flush=True)
+    if not small:
+        for k in ("out_test", "xt_test", "xt_resid", "idx_list"):
+            save.pop(k, None)
+        np.savez_compressed(os.path.join(OUT, tag + ".npz"), **save)
+        print("wrote", tag)
+        return
     test_nu = grid[[3, 11, 29]]
     times, soln = m["B_test"].gpt_test(test_nu, N, NI, NB, IC_u, BC_u, bufs["out"], bufs["out_x"], bufs["out_t"],
                                        bufs["out_xx"], bufs["out_IC"], bufs["out_BC"], f_hat, 1000, lr, neurons,
@@ -305,10 +320,22 @@ def gen_b_small():
 # Allen-Cahn (GPT / precompute path only: AC_main.py itself needs TensorFlow + pyDOE)
 # --------------------------------------------------------------------------------------
 def gen_ac_small():
+    lm = np.linspace(1e-3, 1e-4, 5)
+    ep = np.linspace(1, 5, 5)
+    _gen_ac("ac_small", 800, 64, 20, [1, 3, 9], np.array(np.meshgrid(lm, ep)).T.reshape(-1, 2), 300, 50, True)   # AC_main.py:115-117 ordering
+
+
+def gen_ac_full():
+    """Reference default sizes (AC_main.py:49-51: N_R = 20 000, N_IC = 512, N_BC = 100 per side), n = 9, 2000 epochs."""
+    grid = np.array([[1e-3, 1.0], [7.75e-4, 2.0], [5.5e-4, 4.0], [3.25e-4, 5.0], [1e-4, 3.0], [1e-4, 5.0]])
+    _gen_ac("ac_full", 20000, 512, 100, [9], grid, 2000, 500, False)
+
+
+def _gen_ac(tag, N, NI, NB, ns, grid, epochs, rec, small):
     import scipy.io
     m = _import_ref("Allen-Cahn", ["AC_models", "AC_precompute", "AC_optimizer", "AC_train", "AC_test"])
     rng = np.random.default_rng(0)
-    N, NI, NB, nmax = 800, 64, 20, 9
+    nmax = 9
     data = scipy.io.loadmat(os.path.join(REF, "Allen-Cahn", "AC.mat"))
     x = data["x"].flatten()[:, None]
     t = data["tt"].flatten()[:, None]
@@ -338,7 +365,7 @@ def gen_ac_small():
             w.append((torch.randn(fo, fi, generator=g) * std * 1.2).float())
             b.append((torch.randn(fo, generator=g) * 0.1).float())
         pinn = m["AC_models"].P(w, b, layers)
-        if i < 2:
+        if small and i < 2:
             for l in range(len(layers) - 1):
                 save[f"pinn{i}_W{l}"] = pinn.linears[l].weight.data.numpy().copy()
                 save[f"pinn{i}_b{l}"] = pinn.linears[l].bias.data.numpy().copy()
@@ -351,10 +378,7 @@ def gen_ac_small():
     save.update(xt_resid=xt.detach().numpy(), xt_test=xt_test.numpy(), IC_xt=IC_xt.numpy(),
                 BC_xt_ub=BC_xt_ub.detach().numpy(), BC_xt_lb=BC_xt_lb.detach().numpy(), IC_u=IC_u.numpy(),
                 f_hat=f_hat.numpy())
-    lm = np.linspace(1e-3, 1e-4, 5)
-    ep = np.linspace(1, 5, 5)
-    grid = np.array(np.meshgrid(lm, ep)).T.reshape(-1, 2)          # AC_main.py:115-117 ordering
-    ns, epochs, lr, rec = [1, 3, 9], 300, 0.0025, 50
+    lr = 0.0025
     save.update(grid=grid, ns=np.array(ns), epochs=epochs, lr=lr, rec_every=rec)
     names = ("out", "out_t", "out_xx", "out_IC", "out_BC_ub", "out_BC_lb", "out_BC_diff", "out_BC_ub_x",
              "out_BC_lb_x", "out_BC_diff_x")
@@ -380,7 +404,13 @@ def gen_ac_small():
         save[f"n{n}_L"] = np.float32(float(L))
         save[f"n{n}_case"] = np.array(case, np.float64)
         save[f"n{n}_trained_c"] = tc.numpy()
-        print("ac_small n", n, "L", float(L), "case", case, flush=True)
+        print(tag, "n", n, "L", float(L), "case", case, flush=True)
+    if not small:
+        for k in ("out_test", "xt_test", "xt_resid", "IC_xt", "BC_xt_ub", "BC_xt_lb"):
+            save.pop(k, None)
+        np.savez_compressed(os.path.join(OUT, tag + ".npz"), **save)
+        print("wrote", tag)
+        return
     test_mu = grid[[2, 13, 21]]
     c0 = torch.full((nmax,), 1.0 / nmax)
     args = (bufs["out"], bufs["out_t"], bufs["out_xx"], bufs["out_IC"], f_hat, N, NI, NB, IC_u, c0, 400, lr,
@@ -422,7 +452,7 @@ def gen_kg_greedy():
     print("wrote kg_greedy")
 
 
-GENS = {"kg_small": gen_kg_small, "kg_nonmono": gen_kg_nonmono, "kg_full": gen_kg_full,
+GENS = {"kg_small": gen_kg_small, "kg_nonmono": gen_kg_nonmono, "kg_full": gen_kg_full, "b_full": gen_b_full, "ac_full": gen_ac_full,
         "b_small": gen_b_small, "ac_small": gen_ac_small, "kg_greedy": gen_kg_greedy}
 
 if __name__ == "__main__":

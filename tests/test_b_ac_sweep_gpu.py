@@ -112,3 +112,28 @@ def test_all_n_burgers_ac_against_oracle():
         r = _ac_run(da, n, ga["grid"], torch.full((n,), 1.0 / n, device="cuda"), 80, 0.0025)
         assert rel_scalar(r["f"].cpu().numpy(), o["f"]) < TOL, ("ac", n)
         assert rel_vec(r["c"].cpu().numpy(), o["c"]) < TOL, ("ac", n)
+
+
+def test_burgers_and_allen_cahn_at_reference_default_sizes():
+    """The reference's default problem sizes (Burgers N_R = 10 000 / N_IC = 200 / N_BC = 400, Allen-Cahn N_R = 20 000 /
+    N_IC = 512 / N_BC = 100 per side), n = 9, 2000 epochs: fixtures `b_full`, `ac_full` from the unmodified reference."""
+    from gptpinn import sweep
+    b = load_golden("b_full")
+    d = _dev(b, B_NAMES)
+    n = int(b["ns"][0])
+    r = _b_run(d, n, b["grid"], torch.from_numpy(b[f"n{n}_c0"]).cuda(), int(b["epochs"]), lr_of(b, 0), int(b["rec_every"]))
+    assert rel_scalar(r["f"].cpu().numpy(), b[f"n{n}_f"]) < TOL
+    assert rel_scalar(r["m"].cpu().numpy(), b[f"n{n}_m"]) < TOL
+    assert rel_vec(r["c"].cpu().numpy(), b[f"n{n}_c"]) < TOL
+    assert rel_scalar(r["trace"].cpu().numpy(), b[f"n{n}_trace"]) < TOL
+    L, idx = sweep.argmax_scan(r["f"], r["m"])
+    assert b["grid"][idx] == float(b[f"n{n}_case"]) and abs(float(L) - float(b[f"n{n}_L"])) <= TOL * float(L)
+    a = load_golden("ac_full")
+    d = _dev(a, AC_NAMES)
+    n = int(a["ns"][0])
+    r = _ac_run(d, n, a["grid"], torch.full((n,), 1.0 / n, device="cuda"), int(a["epochs"]), lr_of(a, 0), int(a["rec_every"]))
+    assert rel_scalar(r["f"].cpu().numpy(), a[f"n{n}_f"]) < TOL
+    assert rel_scalar(r["m"].cpu().numpy(), a[f"n{n}_m"]) < TOL
+    assert rel_vec(r["c"].cpu().numpy(), a[f"n{n}_c"]) < TOL
+    L, idx = sweep.argmax_scan(r["f"], r["m"])
+    assert np.array_equal(a["grid"][idx], a[f"n{n}_case"]) and abs(float(L) - float(a[f"n{n}_L"])) <= TOL * float(L)

@@ -80,9 +80,10 @@ def _ac_prob(g, n):
                              g["f_hat"], g["IC_u"])
 
 
+@pytest.mark.parametrize("case", ["b_small", "b_full"])
 @pytest.mark.parametrize("prec", ["f32", "f64"])
-def test_burgers_trajectories_match_reference(prec):
-    g = load_golden("b_small")
+def test_burgers_trajectories_match_reference(prec, case):
+    g = load_golden(case)
     for i, n in enumerate(g["ns"]):
         n = int(n)
         r = oracle.sweep("b", _b_prob(g, n), g["grid"], g[f"n{n}_c0"], int(g["epochs"]), lr_of(g, i),
@@ -97,8 +98,9 @@ def test_burgers_trajectories_match_reference(prec):
 
 
 @pytest.mark.parametrize("prec", ["f32", "f64"])
-def test_allen_cahn_trajectories_match_reference(prec):
-    g = load_golden("ac_small")
+@pytest.mark.parametrize("case", ["ac_small", "ac_full"])
+def test_allen_cahn_trajectories_match_reference(prec, case):
+    g = load_golden(case)
     for i, n in enumerate(g["ns"]):
         n = int(n)
         r = oracle.sweep("ac", _ac_prob(g, n), g["grid"], np.full(n, 1.0 / n, np.float32), int(g["epochs"]),
