@@ -234,3 +234,20 @@ def test_batched_trainer_rejects_bad_batches_without_a_gpu():
         pinn.train_fused_batch(nets * 5, "kg", [(-1.5, 0.5, 0.5)] * 10, *args, xcos=xcos)     # more than MAX_BATCH
     with pytest.raises(_lib.GptPinnError):
         pinn.train_fused_batch(nets, "kg", [(-1.5, 0.5, 0.5)] * 2, *args, xcos=xcos)          # CPU tensors: no fallback
+
+
+def test_header_is_plain_c_and_the_c_demo_links():
+    """include/gptpinn_b200.h is a C header (no C++, no torch types): examples/c_abi_demo.c compiles with gcc and links
+    against the shared library.  (It needs a GPU to run; on a box without one gptpinn_create fails with an error code.)"""
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    out = os.path.join(ROOT, "build", "c_abi_demo")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    libdir = os.path.join(ROOT, "gpt-pinn_b200", "gptpinn", "lib")
+    cmd = ["/usr/bin/gcc", "-O1", "-Wall", "-Werror", "-std=c99", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+           os.path.join(ROOT, "examples", "c_abi_demo.c"), "-o", out, "-L", libdir, "-lgptpinn_b200",
+           "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lm", "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    if not torch.cuda.is_available():
+        run = subprocess.run([out], capture_output=True, text=True)
+        assert run.returncode != 0 and "gptpinn_create" in run.stderr          # fails loudly, no fallback
