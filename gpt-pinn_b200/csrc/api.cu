@@ -67,7 +67,7 @@ static int ensure(void **ptr, size_t *cap, size_t need)
     return GPTPINN_OK;
 }
 
-extern "C" int gptpinn_version(void) { return 100; }
+extern "C" int gptpinn_version(void) { return 200; }
 extern "C" const char *gptpinn_last_error(void) { return g_err; }
 
 extern "C" int gptpinn_create(gptpinn_handle **out)
@@ -260,12 +260,16 @@ static int make_plan(std::vector<ParamRow> &rows, int pde, int n, int n_sm, cons
     const double slot_s = (pde == PDE_KG ? SlotFloats<PDE_KG, RT_SHARED>::value : pde == PDE_B ? SlotFloats<PDE_B, RT_SHARED>::value : SlotFloats<PDE_AC, RT_SHARED>::value) * 4.0;
 
     static const int Ms[4] = {5, 4, 2, 1};
-    const int mode = a->cfg_mode;                     // 0 auto, 1 shared ring, 2 private rings
+    int mode = a->cfg_mode;                           // 0 auto, 1 shared ring, 2 private rings
+    if (a->bound_dev) {                               // early exit leaves the stream at a pass boundary: private rings only
+        if (mode == 1) return fail(GPTPINN_E_INVALID, "bound_dev (early exit) needs the private-ring kernel (cfg_mode 0 or 2)");
+        mode = 2;
+    }
     if (a->cfg_M != 0 && !(a->cfg_M == 1 || a->cfg_M == 2 || a->cfg_M == 4 || a->cfg_M == 5))
         return fail(GPTPINN_E_INVALID, "cfg_M must be 0, 1, 2, 4 or 5");
     if (a->cfg_SL != 0 && (a->cfg_SL < 1 || a->cfg_SL > 32 || (a->cfg_SL & (a->cfg_SL - 1))))
         return fail(GPTPINN_E_INVALID, "cfg_SL must be 0 or a power of two <= 32");
-    if (mode < 0 || mode > 2) return fail(GPTPINN_E_INVALID, "cfg_mode must be 0, 1 or 2");
+    if (a->cfg_mode < 0 || a->cfg_mode > 2) return fail(GPTPINN_E_INVALID, "cfg_mode must be 0, 1 or 2");
 
     if (a->cfg_K != 0 && !(a->cfg_K == 1 || a->cfg_K == 2 || a->cfg_K == 4 || a->cfg_K == 8))
         return fail(GPTPINN_E_INVALID, "cfg_K must be 0, 1, 2, 4 or 8");
@@ -473,6 +477,7 @@ static int run_sweep(gptpinn_handle *h, int pde, int n, const Segments &seg, Pac
     p.rounds = plan.rounds;
     p.counter = h->counter;
     p.K = plan.priv ? plan.K : 1;
+    p.bound = plan.priv ? a->bound_dev : nullptr;
 
     const size_t tblk = (size_t)(n / 4 + 1) * 4 * RT * 4;                       // shared ring only: per-warp T block
     const size_t smem = plan.priv

@@ -80,6 +80,7 @@ struct SweepParams {
     int            W;                // warps per CTA
     int            rounds;           // shared-ring kernels: static rounds of gridDim.x * W items
     unsigned int  *counter;          // private-ring kernels: global work-item ticket (zeroed before launch)
+    const float   *bound;            // private-ring kernels: [Np] per-parameter early-exit bound B_p <= L_seq(p), or nullptr
     int            K;                // private-ring kernels: warps per team (power of two dividing W); a team shares one
                                      // work item, its warps take every K-th tile and sum their gradients once per epoch
 };

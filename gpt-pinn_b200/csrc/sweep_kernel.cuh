@@ -561,27 +561,44 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
             }
             const bool rec = p.trace != nullptr && p.rec_every > 0 && (j % p.rec_every) == 0;
             const bool last = (j == p.epochs);
+            // Early exit (PRIV only; reference KG_train.py:31-33 `if loss < largest_loss: break`): the caller may pass a
+            // per-parameter bound B_p <= L_seq(p).  Once loss_j < B_p for some j < epochs the parameter can
+            // never win the arg-max; it reports f = m = loss_j (the scan then rejects it exactly like the reference's break)
+            // and freezes.  mn < 0 marks a frozen parameter (losses are >= 0; a NaN loss never exits, as in the reference).
+            const bool exiting = PRIV && p.bound != nullptr;
+            bool all_done = exiting;
 #pragma unroll
             for (int m = 0; m < M; ++m) {
                 const float loss = lsum[m];       // = mean_R + mean_IC(s) + mean_BC(s)   (KG_models.py:45-50, B_models.py:42-46, AC_models.py:49-54)
-                if ((rec || last) && slice == 0 && tw == 0 && (sl * M + m) < it.sib_count) {
+                const bool mine = (sl * M + m) < it.sib_count;
+                bool leave = false;
+                if (exiting) {
+                    if (!mine) mn[m] = -1.f;
+                    else if (!last && !(mn[m] < 0.f)) leave = loss < p.bound[p.sibs[it.sib_start + sl * M + m].out_idx];
+                }
+                if ((rec || last || leave) && slice == 0 && tw == 0 && mine && !(mn[m] < 0.f)) {
                     const int oi = p.sibs[it.sib_start + sl * M + m].out_idx;
                     if (rec) p.trace[(size_t)oi * p.nrec + j / p.rec_every] = loss;
-                    if (last) {
+                    if (last || leave) {
                         p.f_out[oi] = loss;
-                        p.m_out[oi] = mn[m];
+                        p.m_out[oi] = leave ? loss : mn[m];
                         if (p.c_out != nullptr) {
 #pragma unroll
                             for (int k = 0; k < N; ++k) p.c_out[(size_t)oi * N + k] = c[m][k];
                         }
                     }
                 }
+                if (leave) mn[m] = -1.f;
+                all_done = all_done && (mn[m] < 0.f);
                 if (!last) {
                     if (loss < mn[m]) mn[m] = loss;
 #pragma unroll
                     for (int k = 0; k < N; ++k) c[m][k] = __fsub_rn(c[m][k], __fmul_rn(p.lr, g[m][k]));
                 }
             }
+            // every lane of the warp (and, after the team sum, every warp of the team) holds the same losses for its
+            // parameters, so the vote is uniform across the team; leaving at a pass boundary keeps the tile ring aligned
+            if (exiting && __all_sync(FULLM, all_done)) break;
         }   // epochs
     }   // items
 

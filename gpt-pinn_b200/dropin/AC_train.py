@@ -11,13 +11,12 @@ def offline_generation(ac_train, c_initial, xt_size, IC_size, BC_size, IC_u,
                        f_hat, epochs_gpt, lr_gpt):
     grid = np.asarray(ac_train, dtype=np.float64).reshape(-1, 2)
 
-    def run(rows, _c0):
+    def run(rows, _c0, epochs=epochs_gpt, bound=None):
         return sweep.ac_sweep(rows, c_initial, out, out_t, out_xx, out_IC, out_BC_ub, out_BC_lb, out_BC_diff,
-                              out_BC_ub_x, out_BC_lb_x, out_BC_diff_x, f_hat, IC_u, epochs_gpt, lr_gpt,
-                              want_c=True)
+                              out_BC_ub_x, out_BC_lb_x, out_BC_diff_x, f_hat, IC_u, epochs, lr_gpt,
+                              want_c=True, bound=bound)
 
-    res = offline.sharded_sweep(run, grid, want_c=True)
-    largest_loss, idx = offline.select(res["f"], res["m"])
+    largest_loss, idx, res = offline.greedy_select(run, grid, epochs_gpt, want_c=True)
     if idx < 0:
         # the reference leaves trained_c unbound here (UnboundLocalError); keep that failure loud
         raise UnboundLocalError("offline_generation: no parameter produced a loss above 0 (trained_c is unbound)")

@@ -2,10 +2,13 @@
 
 Inputs are the tensors the reference passes around (fp32 CUDA tensors, possibly column-slice
 views `out[:, 0:n]` with row stride = number_of_neurons) and the host float64 parameter grid.
-Everything is enqueued on the current torch CUDA stream; only `argmax_scan` (and
-`offline_select`) synchronise, once, to read back (L, index).
+Everything is enqueued on the current torch CUDA stream; `argmax_scan` synchronises once to read back
+(L, index).  The optional targets f_hat / IC_u2 / BC_u are all-zero in every shipped problem and are then
+passed as NULL; whether a tensor is all-zero is checked once per tensor object and version (one tiny
+reduction + sync the first time a given tensor is seen, none afterwards).
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 import torch
@@ -49,10 +52,22 @@ def _vec(t, name, keep, rows):
     return t.data_ptr()
 
 
+_zero_cache = {}
+
+
 def _is_all_zero(t):
     """f_hat / IC_u2 / BC_u are zero in every shipped problem; an all-zero target is passed as NULL so the
-    kernel skips it.  Costs one tiny reduction + host sync per call (not cached: addresses get reused)."""
-    return not bool(torch.any(t != 0).item())
+    kernel skips it.  The answer is cached per tensor object and autograd version counter (in-place writes bump
+    it), so a greedy loop pays the reduction + host sync once per target, not once per call."""
+    ent = _zero_cache.get(id(t))
+    if ent is not None and ent[0]() is t and ent[1] == t._version:
+        return ent[2]
+    res = not bool(torch.any(t != 0).item())
+    if len(_zero_cache) > 256:
+        for k in [k for k, v in _zero_cache.items() if v[0]() is None]:
+            del _zero_cache[k]
+    _zero_cache[id(t)] = (weakref.ref(t), t._version, res)
+    return res
 
 
 def _opt_vec(t, name, keep, rows):
@@ -64,7 +79,7 @@ def _opt_vec(t, name, keep, rows):
     return _vec(t, name, keep, rows)
 
 
-def _run(fn_name, prob, keep, grid, gcols, n, c0, epochs, lr, rec_every, want_c, cfg, device):
+def _run(fn_name, prob, keep, grid, gcols, n, c0, epochs, lr, rec_every, want_c, cfg, device, bound=None):
     grid = np.ascontiguousarray(np.asarray(grid, dtype=np.float64).reshape(-1, gcols))
     Np = grid.shape[0]
     c0 = _req_cuda(c0, "c_initial")
@@ -95,6 +110,11 @@ def _run(fn_name, prob, keep, grid, gcols, n, c0, epochs, lr, rec_every, want_c,
     args.f_out_dev = f.data_ptr()
     args.m_out_dev = m.data_ptr()
     args.trace_dev = trace.data_ptr() if trace is not None else None
+    if bound is not None:
+        bound = _req_cuda(bound, "bound").reshape(-1).contiguous()
+        if bound.numel() != Np:
+            raise ValueError(f"bound has {bound.numel()} entries, expected {Np}")
+        args.bound_dev = bound.data_ptr()
     if cfg:
         args.cfg_M, args.cfg_SL, args.cfg_W = (int(cfg.get("M", 0)), int(cfg.get("SL", 0)), int(cfg.get("W", 0)))
         args.cfg_mode = int(cfg.get("mode", 0))
@@ -105,11 +125,11 @@ def _run(fn_name, prob, keep, grid, gcols, n, c0, epochs, lr, rec_every, want_c,
         stream = torch.cuda.current_stream(device).cuda_stream
         rc = getattr(_lib.lib(), fn_name)(h, C.byref(prob), C.byref(args), C.byref(info), C.c_void_p(stream))
     _lib.check(rc, fn_name)
-    return dict(c=c, f=f, m=m, trace=trace, info=info.asdict(), _keep=(keep, c0, grid))
+    return dict(c=c, f=f, m=m, trace=trace, info=info.asdict(), _keep=(keep, c0, grid, bound))
 
 
 def kg_sweep(grid, c0, out, out_xx, out_tt, out_IC, out_IC_t, out_BC, xcos, f_hat, IC_u1, IC_u2, BC_u,
-             epochs, lr, rec_every=0, want_c=True, cfg=None):
+             epochs, lr, rec_every=0, want_c=True, cfg=None, bound=None):
     """All-epochs Klein-Gordon sweep over `grid` [Np,3] (alpha, beta, gamma)."""
     keep = []
     n = out.shape[1]
@@ -124,11 +144,11 @@ def kg_sweep(grid, c0, out, out_xx, out_tt, out_IC, out_IC_t, out_BC, xcos, f_ha
     p.ICu1 = _vec(IC_u1, "IC_u1", keep, NI)
     p.ICu2 = _opt_vec(IC_u2, "IC_u2", keep, NI)
     p.BCu = _vec(BC_u, "BC_u", keep, NB)
-    return _run("gptpinn_kg_sweep", p, keep, grid, 3, n, c0, epochs, lr, rec_every, want_c, cfg, out.device)
+    return _run("gptpinn_kg_sweep", p, keep, grid, 3, n, c0, epochs, lr, rec_every, want_c, cfg, out.device, bound)
 
 
 def b_sweep(grid, c0, out, out_x, out_t, out_xx, out_IC, out_BC, f_hat, IC_u, BC_u,
-            epochs, lr, rec_every=0, want_c=True, cfg=None):
+            epochs, lr, rec_every=0, want_c=True, cfg=None, bound=None):
     """All-epochs Burgers sweep over `grid` [Np] (nu)."""
     keep = []
     n = out.shape[1]
@@ -141,11 +161,11 @@ def b_sweep(grid, c0, out, out_x, out_t, out_xx, out_IC, out_BC, f_hat, IC_u, BC
     p.fhat = _opt_vec(f_hat, "f_hat", keep, NR)
     p.ICu = _vec(IC_u, "IC_u", keep, NI)
     p.BCu = _opt_vec(BC_u, "BC_u", keep, NB)
-    return _run("gptpinn_b_sweep", p, keep, grid, 1, n, c0, epochs, lr, rec_every, want_c, cfg, out.device)
+    return _run("gptpinn_b_sweep", p, keep, grid, 1, n, c0, epochs, lr, rec_every, want_c, cfg, out.device, bound)
 
 
 def ac_sweep(grid, c0, out, out_t, out_xx, out_IC, out_BC_ub, out_BC_lb, out_BC_diff, out_BC_ub_x,
-             out_BC_lb_x, out_BC_diff_x, f_hat, IC_u, epochs, lr, rec_every=0, want_c=True, cfg=None):
+             out_BC_lb_x, out_BC_diff_x, f_hat, IC_u, epochs, lr, rec_every=0, want_c=True, cfg=None, bound=None):
     """All-epochs Allen-Cahn sweep over `grid` [Np,2] (lambda, eps)."""
     keep = []
     n = out.shape[1]
@@ -160,7 +180,7 @@ def ac_sweep(grid, c0, out, out_t, out_xx, out_IC, out_BC_ub, out_BC_lb, out_BC_
     p.Pdiffx = _mat(out_BC_diff_x, "out_BC_diff_x", keep, n)
     p.fhat = _opt_vec(f_hat, "f_hat", keep, NR)
     p.ICu = _vec(IC_u, "IC_u", keep, NI)
-    return _run("gptpinn_ac_sweep", p, keep, grid, 2, n, c0, epochs, lr, rec_every, want_c, cfg, out.device)
+    return _run("gptpinn_ac_sweep", p, keep, grid, 2, n, c0, epochs, lr, rec_every, want_c, cfg, out.device, bound)
 
 
 def argmax_scan_device(f, m):

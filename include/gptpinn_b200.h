@@ -116,6 +116,13 @@ typedef struct {
     int           cfg_mode;    /* 0 = auto, 1 = shared-ring kernel, 2 = private-ring kernel      */
     int           cfg_K;       /* 0 = auto; private-ring kernel: warps that team up on one work item
                                 * (1, 2, 4 or 8): they split the tiles of a pass and sum their gradients   */
+    /* Optional early exit with the reference's semantics (KG_train.py:31-33 `if loss < largest_loss: break`):
+     * bound_dev[p] must be <= the running maximum the reference's sequential loop holds when it reaches grid
+     * row p (e.g. the max of min(f, m) over already finished rows p' < p).  Row p then stops at the
+     * first j < epochs with loss_j < bound_dev[p] and reports f_out[p] = m_out[p] = loss_j, which
+     * gptpinn_argmax_scan rejects exactly like the reference's break; rows that never fall below their bound
+     * run all epochs and report exact values.  NULL = no early exit (fixed work).  Forces the private-ring kernel. */
+    const float  *bound_dev;   /* [Np] or NULL                                                  */
 } gptpinn_sweep_args;
 
 /* filled by the sweep calls when non-NULL: what was launched (for bench.py / tests)           */
@@ -209,7 +216,7 @@ typedef struct {
 } gptpinn_train_args;
 
 /* `net->W[l]` / `net->b[l]` are updated IN PLACE (contiguous fp32 device tensors).  status_dev[0] = the last
- * evaluated loss (what the reference prints as "PINN Final Loss"), status_dev[1] = epochs entered (float). */
+ * evaluated loss (what the reference prints as "PINN Final Loss"), status_dev[1] = epochs entered, stored as the raw bits of an int32 (read it with memcpy / *(int *)&status[1]). */
 int  gptpinn_pinn_train(gptpinn_handle *h, const gptpinn_pinn_problem *prob, const gptpinn_mlp *net,
                         const gptpinn_train_args *args, float *status_dev, void *stream);
 
