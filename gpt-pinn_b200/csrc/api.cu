@@ -602,6 +602,7 @@ extern "C" int gptpinn_ac_sweep(gptpinn_handle *h, const gptpinn_ac_problem *q, 
     for (int i = 0; i < a->Np; ++i) {
         const double lam = a->grid_host[2 * i], eps = a->grid_host[2 * i + 1];
         rows[i].tp0 = (float)(-lam); rows[i].tp1 = (float)(-eps);       // AC_precompute.py:21-22
+        if (q->t_given) { rows[i].tp0 = 0.f; rows[i].tp1 = 0.f; }       // (T + 0*Pxx) + 0*P == T bit for bit
         rows[i].sp0 = (float)eps; rows[i].sp1 = (float)(3.0 * eps);     // AC_optimizer.py:42,45
         rows[i].idx = i;
     }

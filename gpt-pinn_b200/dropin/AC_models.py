@@ -40,11 +40,11 @@ class GPT(nn.Module):
         return self.loss_function(self.out_IC @ c, self.IC_u)
 
     def loss(self, c):
-        Pt = torch.add(self.Pt_lPxx_eP_term, torch.mul(self.eps, self.out))
+        T = self.Pt_lPxx_eP_term                                 # used bit for bit (t_given)
         grid = np.array([[0.0, float(self.eps)]])
-        r = sweep.ac_sweep(grid, c.reshape(-1), self.out, Pt, Pt, self.out_IC, self.out_BC_ub, self.out_BC_lb,
+        r = sweep.ac_sweep(grid, c.reshape(-1), self.out, T, T, self.out_IC, self.out_BC_ub, self.out_BC_lb,
                            self.out_BC_ub, self.out_BC_ub_x, self.out_BC_lb_x, self.out_BC_ub_x, self.fhat,
-                           self.IC_u, 0, 0.0, want_c=False)
+                           self.IC_u, 0, 0.0, want_c=False, t_given=True)
         return r["f"][0]
 
 

@@ -1,9 +1,8 @@
 """Drop-in for Allen-Cahn/AC_optimizer.py: grad_descent(...).update(c, c_reshaped) -> c
 (reference AC_optimizer.py:4-66).  One update = one single-parameter, single-epoch sweep launch;
-T = P_t - lambda P_xx - eps P is passed as the "P_t" block with lambda = 0 and the eps P term
-removed by handing a zero block for P in the T build (eps still drives the cubic term)."""
+the materialised T = P_t - lambda P_xx - eps P the constructor receives is handed over as is
+(gptpinn_ac_problem.t_given: used bit for bit; eps still drives the cubic term)."""
 import numpy as np
-import torch
 
 from _common import sweep
 
@@ -22,12 +21,11 @@ class grad_descent():
         self.Pt_lPxx_eP_term = Pt_lPxx_eP_term
         self.IC_u = IC_u
         self.lr_gpt = lr_gpt
-        # T_given + eps*P is the "P_t" the kernel needs so that (P_t + 0*P_xx) + (-eps)*P == T_given
-        self._Pt = torch.add(Pt_lPxx_eP_term, torch.mul(eps, out))
         self._grid = np.array([[0.0, float(eps)]])
 
     def update(self, c, c_reshaped):
-        r = sweep.ac_sweep(self._grid, c.reshape(-1), self.out, self._Pt, self._Pt, self.out_IC, self.out_BC_ub,
+        T = self.Pt_lPxx_eP_term
+        r = sweep.ac_sweep(self._grid, c.reshape(-1), self.out, T, T, self.out_IC, self.out_BC_ub,
                            self.out_BC_lb, self.out_BC_diff, self.out_BC_ub_x, self.out_BC_lb_x,
-                           self.out_BC_diff_x, None, self.IC_u, 1, self.lr_gpt, want_c=True)
+                           self.out_BC_diff_x, None, self.IC_u, 1, self.lr_gpt, want_c=True, t_given=True)
         return r["c"][0]

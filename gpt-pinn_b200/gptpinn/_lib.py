@@ -33,7 +33,7 @@ class ACProblem(C.Structure):
     _fields_ = [("n", C.c_int), ("NR", C.c_int), ("NI", C.c_int), ("NB", C.c_int),
                 ("P", Mat), ("Pt", Mat), ("Pxx", Mat), ("PIC", Mat),
                 ("Pub", Mat), ("Plb", Mat), ("Pdiff", Mat), ("Pubx", Mat), ("Plbx", Mat), ("Pdiffx", Mat),
-                ("fhat", C.c_void_p), ("ICu", C.c_void_p)]
+                ("fhat", C.c_void_p), ("ICu", C.c_void_p), ("t_given", C.c_int)]
 
 
 class SweepArgs(C.Structure):

@@ -165,8 +165,10 @@ def b_sweep(grid, c0, out, out_x, out_t, out_xx, out_IC, out_BC, f_hat, IC_u, BC
 
 
 def ac_sweep(grid, c0, out, out_t, out_xx, out_IC, out_BC_ub, out_BC_lb, out_BC_diff, out_BC_ub_x,
-             out_BC_lb_x, out_BC_diff_x, f_hat, IC_u, epochs, lr, rec_every=0, want_c=True, cfg=None, bound=None):
-    """All-epochs Allen-Cahn sweep over `grid` [Np,2] (lambda, eps)."""
+             out_BC_lb_x, out_BC_diff_x, f_hat, IC_u, epochs, lr, rec_every=0, want_c=True, cfg=None, bound=None,
+             t_given=False):
+    """All-epochs Allen-Cahn sweep over `grid` [Np,2] (lambda, eps).  With t_given, `out_t` is the materialised
+    T = P_t - lambda P_xx - eps P (used bit for bit; `out_xx` ignored, only eps of each row is used)."""
     keep = []
     n = out.shape[1]
     NR, NI, NB = out.shape[0], out_IC.shape[0], out_BC_ub.shape[0]
@@ -180,6 +182,7 @@ def ac_sweep(grid, c0, out, out_t, out_xx, out_IC, out_BC_ub, out_BC_lb, out_BC_
     p.Pdiffx = _mat(out_BC_diff_x, "out_BC_diff_x", keep, n)
     p.fhat = _opt_vec(f_hat, "f_hat", keep, NR)
     p.ICu = _vec(IC_u, "IC_u", keep, NI)
+    p.t_given = 1 if t_given else 0
     return _run("gptpinn_ac_sweep", p, keep, grid, 2, n, c0, epochs, lr, rec_every, want_c, cfg, out.device, bound)
 
 

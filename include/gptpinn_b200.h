@@ -85,6 +85,11 @@ typedef struct {
     gptpinn_mat Pubx, Plbx, Pdiffx;      /* out_BC_ub_x/lb_x/diff_x       [NB, n]              */
     const float *fhat;                   /* [NR] or NULL                                       */
     const float *ICu;                    /* [NI]                                               */
+    int t_given;                         /* != 0: `Pt` already holds the materialised operator
+                                          * T = P_t - lambda P_xx - eps P (the Pt_lPxx_eP_term that
+                                          * AC_optimizer.grad_descent / AC_models.GPT receive,
+                                          * AC_optimizer.py:4-20): it is used as is (bit-exact), `Pxx`
+                                          * is ignored and only eps of each grid row is used          */
 } gptpinn_ac_problem;
 
 /* What one sweep call does for each of the Np grid rows (parameters):

@@ -452,8 +452,168 @@ def gen_kg_greedy():
     print("wrote kg_greedy")
 
 
+# --------------------------------------------------------------------------------------
+# single-step classes: grad_descent.update / GPT.loss(+ partial losses) of all three PDEs, as user code drives them
+# --------------------------------------------------------------------------------------
+def gen_classes():
+    """One reference `update` and every reference loss method on the matrices of the *_small fixtures (loaded back
+    from tests/golden), for a few parameters and neuron counts, from seeded random c."""
+    save = {}
+    rng = np.random.default_rng(99)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    # ---- Klein-Gordon (KG_optimizer.py:4-68, KG_models.py:7-50)
+    m = _import_ref("Klein-Gordon", ["KG_models", "KG_precomp", "KG_optimizer"])
+    g = np.load(os.path.join(OUT, "kg_small.npz"))
+    N, NI, NB = g["out"].shape[0], g["out_IC"].shape[0], g["out_BC"].shape[0]
+    for n in (2, 7, 15):
+        v = {k: t(g[k])[:, :n] for k in ("out", "out_xx", "out_tt", "out_IC", "out_IC_t", "out_BC")}
+        mus = g["grid"][[5, 33, 59]]
+        cin = (rng.standard_normal((len(mus), n)) * 0.4).astype(np.float32)
+        cout, L = np.zeros_like(cin), np.zeros((len(mus), 5), np.float32)
+        for k, (a, b, gm) in enumerate(mus):
+            T = m["KG_precomp"].Ptt_aPxx_bP(a, b, v["out_tt"], v["out_xx"], v["out"])
+            G2 = m["KG_precomp"].gamma2_P(gm, v["out"])
+            GD = m["KG_optimizer"].grad_descent(a, b, gm, N, NI, NB, t(g["IC_u1"]), t(g["IC_u2"]), t(g["BC_u"]), t(g["xcos"]), T, G2,
+                                                v["out"], v["out_IC"], v["out_IC_t"], v["out_BC"], 1, 0.025)
+            NNg = m["KG_models"].GPT(a, b, gm, v["out"], v["out_IC"], v["out_IC_t"], v["out_BC"], t(g["xcos"]), t(g["f_hat"]), T,
+                                     t(g["IC_u1"]), t(g["IC_u2"]), t(g["BC_u"]))
+            c = t(cin[k])
+            cout[k] = GD.update(c, c.unsqueeze(1)).numpy()
+            cr = c.unsqueeze(1)
+            L[k] = [NNg.loss(cr).item(), NNg.lossR(cr).item(), NNg.lossIC1(cr).item(), NNg.lossIC2(cr).item(), NNg.lossBC(cr).item()]
+        save.update({f"kg_n{n}_mu": mus, f"kg_n{n}_cin": cin, f"kg_n{n}_cout": cout, f"kg_n{n}_loss": L})
+    # ---- Burgers (B_optimizer.py:4-58, B_models.py:11-46)
+    m = _import_ref("Burgers", ["B_models", "B_precomp", "B_optimizer"])
+    g = np.load(os.path.join(OUT, "b_small.npz"))
+    N, NI, NB = g["out"].shape[0], g["out_IC"].shape[0], g["out_BC"].shape[0]
+    for n in (2, 9):
+        v = {k: t(g[k])[:, :n] for k in ("out", "out_t", "out_x", "out_xx", "out_IC", "out_BC")}
+        mus = g["grid"][[1, 17, 30]]
+        cin = (rng.standard_normal((len(mus), n)) * 0.4).astype(np.float32)
+        cout, L = np.zeros_like(cin), np.zeros((len(mus), 4), np.float32)
+        for k, nu in enumerate(mus):
+            T = m["B_precomp"].Pt_nu_P_xx(nu, v["out_t"], v["out_xx"])
+            GD = m["B_optimizer"].grad_descent(nu, N, NI, NB, t(g["IC_u"]), v["out"], v["out_IC"], v["out_BC"], v["out_x"], T, 0.02)
+            NNg = m["B_models"].GPT(nu, v["out"], v["out_IC"], v["out_BC"], v["out_x"], T, t(g["IC_u"]), t(g["BC_u"]), t(g["f_hat"]))
+            c = t(cin[k])
+            cout[k] = GD.update(c, c.unsqueeze(1)).numpy()
+            cr = c.unsqueeze(1)
+            L[k] = [NNg.loss(cr).item(), NNg.lossR(cr).item(), NNg.lossIC(cr).item(), NNg.lossBC(cr).item()]
+        save.update({f"b_n{n}_mu": mus, f"b_n{n}_cin": cin, f"b_n{n}_cout": cout, f"b_n{n}_loss": L})
+    # ---- Allen-Cahn (AC_optimizer.py:4-66, AC_models.py:6-54)
+    m = _import_ref("Allen-Cahn", ["AC_models", "AC_precompute", "AC_optimizer"])
+    g = np.load(os.path.join(OUT, "ac_small.npz"))
+    N, NI, NB = g["out"].shape[0], g["out_IC"].shape[0], g["out_BC_ub"].shape[0]
+    names = ("out", "out_t", "out_xx", "out_IC", "out_BC_ub", "out_BC_lb", "out_BC_diff", "out_BC_ub_x", "out_BC_lb_x", "out_BC_diff_x")
+    for n in (3, 9):
+        v = {k: t(g[k])[:, :n] for k in names}
+        mus = g["grid"][[0, 12, 24]]
+        cin = (rng.standard_normal((len(mus), n)) * 0.4).astype(np.float32)
+        cout, L = np.zeros_like(cin), np.zeros((len(mus), 5), np.float32)
+        for k, (lam, eps) in enumerate(mus):
+            T = m["AC_precompute"].Pt_lPxx_eP(v["out_t"], v["out_xx"], v["out"], lam, eps)
+            GD = m["AC_optimizer"].grad_descent(lam, eps, N, NI, NB, t(g["IC_u"]), T, v["out"], v["out_IC"], v["out_BC_ub"], v["out_BC_lb"],
+                                                v["out_BC_diff"], v["out_BC_ub_x"], v["out_BC_lb_x"], v["out_BC_diff_x"], 1, 0.0025)
+            NNg = m["AC_models"].GPT(lam, eps, v["out"], v["out_IC"], v["out_BC_ub"], v["out_BC_lb"], v["out_BC_ub_x"], v["out_BC_lb_x"],
+                                     t(g["f_hat"]), T, t(g["IC_u"]))
+            c = t(cin[k])
+            cout[k] = GD.update(c, c.unsqueeze(1)).numpy()
+            cr = c.unsqueeze(1)
+            L[k] = [NNg.loss(cr).item(), NNg.lossR(cr).item(), NNg.lossIC(cr).item(), NNg.lossBC(cr).item(), NNg.lossBC_x(cr).item()]
+        save.update({f"ac_n{n}_mu": mus, f"ac_n{n}_cin": cin, f"ac_n{n}_cout": cout, f"ac_n{n}_loss": L})
+    np.savez_compressed(os.path.join(OUT, "classes.npz"), **save)
+    print("wrote classes")
+
+
+# --------------------------------------------------------------------------------------
+# full-PINN training step: the reference's NN.loss + torch.optim.Adam (SURVEY.md 8c item 5)
+# --------------------------------------------------------------------------------------
+def _flat(params):
+    return np.concatenate([p.detach().numpy().reshape(-1) for p in params])
+
+
+def _pinn_fixture(make, loss_of, lr, steps, tol=None):
+    """loss, all gradients, weights after one Adam step, and a `steps`-long loss trace (loss BEFORE each step, as the
+    reference's loop evaluates it); plus the same loss / gradient in float64 (autograd in double on the same
+    weights) so the tests can state how far fp32 autograd itself sits from the exact value."""
+    net = make()
+    params = [q for lin in net.linears for q in (lin.weight, lin.bias)]
+    w0 = _flat(params)
+    opt = torch.optim.Adam(net.parameters(), lr=lr)
+    loss = loss_of(net, torch.float32)
+    opt.zero_grad()
+    loss.backward()
+    g32 = _flat([q.grad for q in params])
+    opt.step()
+    w1 = _flat(params)
+    trace = [loss.item()]
+    for _ in range(steps - 1):
+        loss = loss_of(net, torch.float32)
+        if tol is not None and loss < tol:
+            break
+        trace.append(loss.item())
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    wN = _flat(params)
+    final = loss_of(net, torch.float32).item()
+    net64 = make().double()
+    loss64 = loss_of(net64, torch.float64)
+    loss64.backward()
+    g64 = _flat([q.grad for lin in net64.linears for q in (lin.weight, lin.bias)])
+    return dict(w0=w0, loss=np.float32(trace[0]), grad=g32, w1=w1, trace=np.array(trace, np.float32), wN=wN,
+                final_loss=np.float32(final), loss64=np.float64(loss64.item()), grad64=g64)
+
+
+def gen_pinn_step():
+    save = {}
+    # ---- Klein-Gordon: NN([2,40,40,1], cos), the constructor's own seed-1234 Xavier init (KG_models.py:62-82)
+    m = _import_ref("Klein-Gordon", ["KG_data", "KG_models", "KG_precomp"])
+    for tag, (Nc, ICp, BCp), steps in (("kg_small", (24, 64, 64), 200), ("kg_default", (100, 512, 512), 40)):
+        xt, f_hat, _ = m["KG_data"].residual_data(-1.0, 1.0, 0.0, 5.0, Nc, 4)
+        IC_xt, IC_u1, IC_u2, BC_xt, BC_u = m["KG_data"].ICBC_data(-1.0, 1.0, 0.0, 5.0, BCp, ICp)
+        xcos = m["KG_precomp"].xcos_term(xt[:, 0].unsqueeze(1), xt[:, 1].unsqueeze(1))
+        mu = (-1.3, 0.4, 0.7)
+
+        def make():
+            return m["KG_models"].NN(np.array([2, 40, 40, 1]), *mu, xcos)
+
+        def loss_of(net, dt):
+            net.xcos_x2cos2 = xcos.to(dt)
+            a = xt.to(dt).clone().requires_grad_()
+            b = IC_xt.to(dt).clone().requires_grad_()
+            return net.loss(a, f_hat.to(dt), b, IC_u1.to(dt), IC_u2.to(dt), BC_xt.to(dt), BC_u.to(dt))
+        r = _pinn_fixture(make, loss_of, 5e-4, steps)
+        save.update({f"{tag}_{k}": v for k, v in r.items()})
+        save[f"{tag}_sizes"] = np.array([Nc, ICp, BCp])
+        save[f"{tag}_mu"] = np.array(mu)
+        save[f"{tag}_lr"] = 5e-4
+        print(tag, "loss", r["loss"], "loss64", r["loss64"], "|g32-g64|max/|g|max", np.abs(r["grad"] - r["grad64"]).max() / np.abs(r["grad64"]).max(), flush=True)
+    # ---- Burgers: NN([2,20,20,20,20,1], tanh) (B_models.py:52-105), lr 5e-3, tolerance semantics of B_train.py:84
+    m = _import_ref("Burgers", ["B_data", "B_models"])
+    for tag, (Nc, ICp, BCp), steps in (("b_small", (24, 40, 40), 200), ("b_default", (100, 200, 200), 40)):
+        xt, f_hat, _ = m["B_data"].residual_data(-1.0, 1.0, 0.0, 1.0, Nc, 4)
+        IC_xt, IC_u, BC_xt, BC_u = m["B_data"].ICBC_data(-1.0, 1.0, 0.0, 1.0, BCp, ICp)
+        nu = 0.05
+
+        def make():
+            return m["B_models"].NN(np.array([2, 20, 20, 20, 20, 1]), nu)
+
+        def loss_of(net, dt):
+            a = xt.to(dt).clone().requires_grad_()
+            return net.loss(a, IC_xt.to(dt), IC_u.to(dt), BC_xt.to(dt), BC_u.to(dt), f_hat.to(dt))
+        r = _pinn_fixture(make, loss_of, 5e-3, steps)
+        save.update({f"{tag}_{k}": v for k, v in r.items()})
+        save[f"{tag}_sizes"] = np.array([Nc, ICp, BCp])
+        save[f"{tag}_mu"] = np.array([nu])
+        save[f"{tag}_lr"] = 5e-3
+        print(tag, "loss", r["loss"], "loss64", r["loss64"], "|g32-g64|max/|g|max", np.abs(r["grad"] - r["grad64"]).max() / np.abs(r["grad64"]).max(), flush=True)
+    np.savez_compressed(os.path.join(OUT, "pinn_step.npz"), **save)
+    print("wrote pinn_step")
+
+
 GENS = {"kg_small": gen_kg_small, "kg_nonmono": gen_kg_nonmono, "kg_full": gen_kg_full, "b_full": gen_b_full, "ac_full": gen_ac_full,
-        "b_small": gen_b_small, "ac_small": gen_ac_small, "kg_greedy": gen_kg_greedy}
+        "b_small": gen_b_small, "ac_small": gen_ac_small, "kg_greedy": gen_kg_greedy, "classes": gen_classes, "pinn_step": gen_pinn_step}
 
 if __name__ == "__main__":
     torch.set_num_threads(int(os.environ.get("OMP_NUM_THREADS", "8")))

@@ -201,8 +201,8 @@ def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, OMP_NUM_THREADS="4")
-    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                       capture_output=True, text=True, timeout=600, env=env)
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--epochs", "200", "--ref-sample", "4,100,6"], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -214,6 +214,8 @@ def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["higher_is_better"] is True and d["value"] > 0 and d["gpu_launches"] == 0
     assert "workload" in d["config"]
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"])
+    assert d["cpu_baseline"]["kind"] == "reference"          # the unmodified reference (oracle/_ref), not a port
+    assert d["reference"]["offline_generation_early_exit"]["rows"] == 6
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
 
 
