@@ -249,6 +249,182 @@ static cudaError_t launch_tile(const MlpDesc &d, const float *xt, long long N, c
     return cudaLaunchKernel(kern, dim3(blocks), dim3(TNG * 32), args, smem, st);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Wide networks (hidden width 41..128: Allen-Cahn's [2,128,128,128,128,1] tanh shell, AC_models.py:56-78).
+// A CTA of 256 threads takes a tile of 64 points.  The activations of all 128 (padded) neurons, all channels, live in
+// shared memory as A[neuron][channel][point]; every hidden->hidden layer is a [128 x 128] x [128 x CH*64] GEMM done
+// in registers: thread (jg, cg) owns 8 output neurons x (CH channels x 4 points) and walks the 128 inputs four at a
+// time -- per 4 inputs it reads 8 float4 of the layer's weight matrix (row-major as torch stores it; the 16 threads
+// that share jg broadcast) and 4*CH float4 of activations (conflict-free: a warp reads 64 consecutive points), i.e.
+// 32*CH FMAs per (2 + CH) LDS.128.  The activation function then maps the channels of the thread's own (neuron, point)
+// pairs in registers and writes them back in place.  Weights of one layer at a time are staged in shared memory
+// (64 KB, L2-resident source).  Channels: CH = 1 (v), 3 (v, x, t) or 4 (v, x, t, q = u_xx + u_xt); the r channel of a
+// wide network goes through the one-thread-per-point kernel above (no shipped problem needs it).
+// ---------------------------------------------------------------------------------------------------
+constexpr int WW = 128, WPTS = 64, WTHREADS = 256;
+
+template <int CH>
+__global__ void __launch_bounds__(WTHREADS, 1) mlp_channels_wide_kernel(const MlpDesc d, const float *__restrict__ xt, long long N, const MlpOut o)
+{
+    extern __shared__ __align__(16) float smw[];
+    float *A_s = smw;                                   // [WW][CH][WPTS]
+    float *W_s = A_s + WW * CH * WPTS;                  // [WW][WW] row-major [out j][in i], zero padded; later the output partials
+    const int tid = threadIdx.x, jg = tid >> 4, cg = tid & 15, j0 = 8 * jg, p0 = 4 * cg;
+    const int NH = d.nlayers - 2;
+    const long long ntiles = (N + WPTS - 1) / WPTS;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        float acc[8][CH][4];
+        // ---- layer 0: inputs (x, t); channels of z known in closed form
+        {
+            float xs[4], ts[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const long long p = tile * WPTS + p0 + k;
+                xs[k] = p < N ? xt[2 * p] : 0.f;
+                ts[k] = p < N ? xt[2 * p + 1] : 0.f;
+            }
+            const int w1 = d.layers[1];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const int j = j0 + jj;
+                const bool ok = j < w1;
+                const float wx = ok ? d.W[0][2 * j] : 0.f, wt = ok ? d.W[0][2 * j + 1] : 0.f, bb = ok ? d.b[0][j] : 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    acc[jj][0][k] = fmaf(wx, xs[k], fmaf(wt, ts[k], bb));
+                    if constexpr (CH >= 3) { acc[jj][1][k] = wx; acc[jj][2][k] = wt; }
+                    if constexpr (CH >= 4) acc[jj][3][k] = 0.f;
+                }
+            }
+        }
+        for (int l = 0; l < NH; ++l) {
+            // ---- activation of hidden layer l on the thread's own (neuron, point) pairs, written to A in place
+            const int wl = d.layers[l + 1];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const bool ok = (j0 + jj) < wl;
+                float a[CH][4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float z0 = acc[jj][0][k];
+                    float s0, s1, s2;
+                    if (d.act == 0) { float sn, cs; sincosf(z0, &sn, &cs); s0 = cs; s1 = -sn; s2 = -cs; }
+                    else { s0 = tanhf(z0); s1 = 1.f - s0 * s0; s2 = -2.f * s0 * s1; }
+                    a[0][k] = ok ? s0 : 0.f;
+                    if constexpr (CH >= 3) {
+                        const float zx = acc[jj][1][k], zt = acc[jj][2][k];
+                        a[1][k] = ok ? s1 * zx : 0.f;
+                        a[2][k] = ok ? s1 * zt : 0.f;
+                        if constexpr (CH >= 4) a[3][k] = ok ? fmaf(s2 * zx, zx + zt, s1 * acc[jj][3][k]) : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < CH; ++c)
+                    *reinterpret_cast<float4 *>(A_s + ((j0 + jj) * CH + c) * WPTS + p0) = make_float4(a[c][0], a[c][1], a[c][2], a[c][3]);
+            }
+            if (l == NH - 1) break;
+            // ---- stage the weights of the map hidden l -> hidden l+1 (torch layout [out][in]), zero padded to 128 x 128
+            {
+                const int wi = d.layers[l + 1], wo = d.layers[l + 2];
+                const float *Wg = d.W[l + 1];
+                for (int e = tid; e < WW * WW; e += WTHREADS) {
+                    const int j = e >> 7, i = e & 127;
+                    W_s[e] = (j < wo && i < wi) ? Wg[j * wi + i] : 0.f;
+                }
+            }
+            __syncthreads();                              // A (all neurons) and W are in place
+            {
+                const int wo = d.layers[l + 2];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const float bb = (j0 + jj) < wo ? d.b[l + 1][j0 + jj] : 0.f;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        acc[jj][0][k] = bb;
+#pragma unroll
+                        for (int c = 1; c < CH; ++c) acc[jj][c][k] = 0.f;
+                    }
+                }
+            }
+#pragma unroll 1
+            for (int i4 = 0; i4 < WW; i4 += 4) {
+                float4 wq[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) wq[jj] = *reinterpret_cast<const float4 *>(W_s + (j0 + jj) * WW + i4);
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) {
+                    float4 av[CH];
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) av[c] = *reinterpret_cast<const float4 *>(A_s + ((i4 + ii) * CH + c) * WPTS + p0);
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const float w = ii == 0 ? wq[jj].x : (ii == 1 ? wq[jj].y : (ii == 2 ? wq[jj].z : wq[jj].w));
+#pragma unroll
+                        for (int c = 0; c < CH; ++c) {
+                            acc[jj][c][0] = fmaf(w, av[c].x, acc[jj][c][0]);
+                            acc[jj][c][1] = fmaf(w, av[c].y, acc[jj][c][1]);
+                            acc[jj][c][2] = fmaf(w, av[c].z, acc[jj][c][2]);
+                            acc[jj][c][3] = fmaf(w, av[c].w, acc[jj][c][3]);
+                        }
+                    }
+                }
+            }
+            __syncthreads();                              // every read of A and W is done: both may be overwritten
+        }
+        __syncthreads();                                  // A holds the activations of the last hidden layer
+        // ---- output unit: partial over the thread's 8 neurons, then over the 16 neuron groups through shared memory
+        {
+            const int wl = d.layers[NH];
+            float pu[CH][4];
+#pragma unroll
+            for (int c = 0; c < CH; ++c)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) pu[c][k] = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const float w = (j0 + jj) < wl ? d.W[NH][j0 + jj] : 0.f;
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    const float4 a = *reinterpret_cast<const float4 *>(A_s + ((j0 + jj) * CH + c) * WPTS + p0);
+                    pu[c][0] = fmaf(w, a.x, pu[c][0]); pu[c][1] = fmaf(w, a.y, pu[c][1]);
+                    pu[c][2] = fmaf(w, a.z, pu[c][2]); pu[c][3] = fmaf(w, a.w, pu[c][3]);
+                }
+            }
+            float *R = W_s;                               // [16 jg][CH][WPTS]
+#pragma unroll
+            for (int c = 0; c < CH; ++c)
+                *reinterpret_cast<float4 *>(R + (jg * CH + c) * WPTS + p0) = make_float4(pu[c][0], pu[c][1], pu[c][2], pu[c][3]);
+            __syncthreads();
+            for (int e = tid; e < CH * WPTS; e += WTHREADS) {
+                const int c = e / WPTS, k = e % WPTS;
+                const long long p = tile * WPTS + k;
+                float s = c == 0 ? d.b[NH][0] : 0.f;
+#pragma unroll
+                for (int g = 0; g < 16; ++g) s += R[(g * CH + c) * WPTS + k];
+                if (p < N && o.ptr[c]) o.ptr[c][p * o.ld[c]] = s;
+            }
+            __syncthreads();                              // R (= W_s) and A are rewritten by the next tile
+        }
+    }
+}
+
+template <int CH>
+static cudaError_t launch_wide(const MlpDesc &d, const float *xt, long long N, const MlpOut &o, cudaStream_t st)
+{
+    const size_t smem = ((size_t)WW * CH * WPTS + (size_t)WW * WW) * sizeof(float);
+    auto kern = mlp_channels_wide_kernel<CH>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, nsm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const long long ntiles = (N + WPTS - 1) / WPTS;
+    const unsigned blocks = (unsigned)(ntiles < nsm ? ntiles : nsm);
+    kern<<<blocks, WTHREADS, smem, st>>>(d, xt, N, o);
+    return cudaGetLastError();
+}
+
 template <int WMAX>
 static cudaError_t launch_w(const MlpDesc &d, const float *xt, long long N, const MlpOut &o, int ch, size_t smem, cudaStream_t st)
 {
@@ -293,6 +469,11 @@ cudaError_t launch_mlp_channels(const MlpDesc &d, const float *xt, long long N, 
         if (nh == 1) return launch_tile<40, 1>(d, xt, N, o, ch, st);
         if (nh == 2) return launch_tile<40, 2>(d, xt, N, o, ch, st);
         if (nh == 3) return launch_tile<40, 3>(d, xt, N, o, ch, st);
+    }
+    if (nh >= 1 && maxh > 40 && maxh <= WW && !o.ptr[4]) {       // wide hidden layers (Allen-Cahn): tiled register GEMM
+        if (o.ptr[3]) return launch_wide<4>(d, xt, N, o, st);
+        if (o.ptr[1] || o.ptr[2]) return launch_wide<3>(d, xt, N, o, st);
+        return launch_wide<1>(d, xt, N, o, st);
     }
     if (maxw <= 20) return launch_w<20>(d, xt, N, o, ch, smem, st);
     if (maxw <= 40) return launch_w<40>(d, xt, N, o, ch, smem, st);
