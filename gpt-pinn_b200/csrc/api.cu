@@ -735,6 +735,7 @@ extern "C" int gptpinn_pinn_train_batch(gptpinn_handle *h, int nbatch, const gpt
     d.invR = (float)(1.0 / q->NR); d.invI = (float)(1.0 / q->NI); d.invB = (float)(1.0 / q->NB);
     d.epochs = ta->epochs;
     d.lr = (float)ta->lr; d.beta1 = (float)ta->beta1; d.beta2 = (float)ta->beta2;
+    d.lr_d = ta->lr; d.beta1_d = ta->beta1; d.beta2_d = ta->beta2;
     d.omb1 = (float)(1.0 - ta->beta1); d.omb2 = (float)(1.0 - ta->beta2); d.eps = (float)ta->eps;
     d.tol = ta->tol >= 0 ? (float)ta->tol : -1.f;
     d.trace_every = ta->trace_every;

@@ -444,9 +444,9 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
         __syncthreads();
         const bool stop = d.tol >= 0.f && U_s[0] < d.tol;                 // B_train.py:84: break before the step
         if (!stop) {
-            const double bc1 = 1.0 - pow((double)d.beta1, (double)epoch);
-            const double bc2 = 1.0 - pow((double)d.beta2, (double)epoch);
-            const float step_size = (float)((double)d.lr / bc1);
+            const double bc1 = 1.0 - pow(d.beta1_d, (double)epoch);       // torch.optim.Adam: bias corrections in double from the
+            const double bc2 = 1.0 - pow(d.beta2_d, (double)epoch);       // Python floats (0.9, 0.999), not from their fp32 roundings
+            const float step_size = (float)(d.lr_d / bc1);
             const float bc2_sqrt = (float)sqrt(bc2);
             // gradient reduction: 8 lanes per parameter, fixed order (deterministic), then torch.optim.Adam
             const int gthreads = gsz * blockDim.x;

@@ -23,9 +23,10 @@ struct PinnDesc {
     float invR, invI, invB;
     int epochs;
     float lr, beta1, beta2, omb1, omb2, eps;  // omb = (float)(1 - beta) as torch forms it in double
+    double beta1_d, beta2_d, lr_d;            // the Python doubles torch.optim.Adam forms its bias corrections from
     float tol;                                // < 0: no tolerance stop
     float *partials; int n_partials; int partial_stride;   // [n_partials][partial_stride >= n_params + 4]
-    float *status;                            // [2]: last evaluated loss, epochs executed (as int bits)
+    float *status;                            // [2]: last evaluated loss, epochs entered (raw int32 bits)
     int *stop;                                // [1]
     float *loss_trace; int trace_every;       // optional: loss before the step of epochs 1, 1+k, ...
 };

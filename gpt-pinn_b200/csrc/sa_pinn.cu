@@ -1,0 +1,264 @@
+// sa_pinn.cu -- device kernels of the self-adaptive PINN trainer for Allen-Cahn (C ABI: gptpinn_sa_*).
+//
+// Reference: the TensorFlow trainer in Allen-Cahn/AC_main.py:204-339 (= AC_SA_test.py:109-245): tanh MLP
+// [2,128,128,128,128,1]; loss = mean((w_u (u0 - u(x,0)))^2) + mean((u_lb - u_ub)^2) + mean((u_x,lb - u_x,ub)^2)
+// + mean((w_f f)^2) with f = u_t - lambda u_xx + eps u^3 - eps u (true u_xx, :235-244); Adam(lr 5e-3, beta1 0.99) descent
+// on the network weights and ASCENT on the self-adaptive weights w_f [N_f,1], w_u [N_0,1] (:297-298); then fixed-step
+// L-BFGS on the weights.  TensorFlow differentiates that loss three levels deep; here the four channels
+// (u, u_x, u_t, u_xx) are propagated forward in closed form and the reverse pass is hand-derived:
+//   a = tanh(z):  a_x = s1 z_x,  a_t = s1 z_t,  a_xx = s2 z_x^2 + s1 z_xx        (s1 = 1 - a^2, s2 = -2 a s1, s3 = s1 (6 a^2 - 2))
+//   zbar_xx = s1 abar_xx,  zbar_t = s1 abar_t,  zbar_x = s1 abar_x + 2 s2 z_x abar_xx,
+//   zbar_u  = s1 abar_u + s2 (z_x abar_x + z_t abar_t + z_xx abar_xx) + s3 z_x^2 abar_xx
+// All points (collocation, initial, lower / upper boundary) run as ONE batch of N points; tensors are [4][N][W]
+// (channel-major, W = hidden width), so every hidden->hidden map of all four channels is one [4N x W] x [W x W] GEMM
+// -- a plain library GEMM (cuBLAS through torch.mm on the host side, gptpinn/sa_pinn.py); everything else is here.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "../../include/gptpinn_b200.h"
+
+namespace gp {
+
+__global__ void sa_layer0_kernel(const float *__restrict__ xt, const float *__restrict__ W0, const float *__restrict__ b0,
+                                 long long N, int W, float *__restrict__ Z)
+{
+    const long long total = N * W, plane = total;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long p = e / W;
+        const int j = (int)(e % W);
+        const float wx = W0[2 * j], wt = W0[2 * j + 1];
+        Z[e] = fmaf(wx, xt[2 * p], fmaf(wt, xt[2 * p + 1], b0[j]));
+        Z[plane + e] = wx;
+        Z[2 * plane + e] = wt;
+        Z[3 * plane + e] = 0.f;
+    }
+}
+
+// Z[0] += bias (stored back: the reverse pass needs the pre-activation), A = channels of tanh(Z)
+__global__ void sa_act_forward_kernel(float *__restrict__ Z, const float *__restrict__ bias, float *__restrict__ A, long long N, int W)
+{
+    const long long total = N * W, plane = total;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        float z0 = Z[e];
+        if (bias) { z0 += bias[(int)(e % W)]; Z[e] = z0; }
+        const float zx = Z[plane + e], zt = Z[2 * plane + e], zxx = Z[3 * plane + e];
+        const float s0 = tanhf(z0), s1 = 1.f - s0 * s0, s2 = -2.f * s0 * s1;
+        A[e] = s0;
+        A[plane + e] = s1 * zx;
+        A[2 * plane + e] = s1 * zt;
+        A[3 * plane + e] = fmaf(s2 * zx, zx, s1 * zxx);
+    }
+}
+
+// G: adjoint of the activations on entry, adjoint of the pre-activations on return
+__global__ void sa_act_backward_kernel(const float *__restrict__ Z, float *__restrict__ G, long long N, int W)
+{
+    const long long total = N * W, plane = total;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const float z0 = Z[e], zx = Z[plane + e], zt = Z[2 * plane + e], zxx = Z[3 * plane + e];
+        const float a0 = G[e], a1 = G[plane + e], a2 = G[2 * plane + e], a3 = G[3 * plane + e];
+        const float s0 = tanhf(z0), s1 = 1.f - s0 * s0, s2 = -2.f * s0 * s1, s3 = s1 * (6.f * s0 * s0 - 2.f);
+        G[3 * plane + e] = s1 * a3;
+        G[2 * plane + e] = s1 * a2;
+        G[plane + e] = fmaf(s1, a1, 2.f * s2 * zx * a3);
+        G[e] = s1 * a0 + s2 * (zx * a1 + zt * a2 + zxx * a3) + s3 * zx * zx * a3;
+    }
+}
+
+// U[c][p] = sum_j A[c][p][j] Wout[j] (+ bout on channel 0): one warp per (c, p) row
+__global__ void sa_output_forward_kernel(const float *__restrict__ A, const float *__restrict__ Wout, const float *__restrict__ bout,
+                                         long long N, int W, float *__restrict__ U)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < 4 * N; row += warps) {
+        const float *a = A + row * W;
+        float s = 0.f;
+        for (int j = lane; j < W; j += 32) s = fmaf(a[j], Wout[j], s);
+        for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) U[row] = s + (row < N ? bout[0] : 0.f);
+    }
+}
+
+constexpr int SA_LOSS_BLOCKS = 128, SA_LOSS_THREADS = 256, SA_NSUM = 6;
+
+// points are ordered [collocation NR | initial NI | lower boundary NB | upper boundary NB]; partial sums per block
+__global__ void __launch_bounds__(SA_LOSS_THREADS) sa_loss_kernel(const float *__restrict__ U, long long N, int NR, int NI, int NB,
+                                                                  const float *__restrict__ u0, const float *__restrict__ wf,
+                                                                  const float *__restrict__ wu, float lam, float eps,
+                                                                  float *__restrict__ Ubar, float *__restrict__ gwf, float *__restrict__ gwu,
+                                                                  float *__restrict__ partial)
+{
+    float s[SA_NSUM] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // (wu r)^2, r^2, dv^2, dx^2, (wf f)^2, f^2
+    const float *u = U, *ux = U + N, *ut = U + 2 * N, *uxx = U + 3 * N;
+    float *bu = Ubar, *bx = Ubar + N, *bt = Ubar + 2 * N, *bxx = Ubar + 3 * N;
+    const int work = NR + NI + NB;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < work; p += gridDim.x * blockDim.x) {
+        if (p < NR) {
+            const float uu = u[p];
+            const float f = ut[p] - lam * uxx[p] + eps * uu * uu * uu - eps * uu;        // AC_main.py:243
+            const float w = wf[p];
+            const float df = 2.f * w * w * f / (float)NR;
+            bu[p] = (3.f * eps * uu * uu - eps) * df; bx[p] = 0.f; bt[p] = df; bxx[p] = -lam * df;
+            gwf[p] = 2.f * w * f * f / (float)NR;
+            s[4] = fmaf(w * f, w * f, s[4]); s[5] = fmaf(f, f, s[5]);
+        } else if (p < NR + NI) {
+            const int i = p - NR;
+            const float r = u0[i] - u[p], w = wu[i];
+            bu[p] = -2.f * w * w * r / (float)NI; bx[p] = 0.f; bt[p] = 0.f; bxx[p] = 0.f;
+            gwu[i] = 2.f * w * r * r / (float)NI;
+            s[0] = fmaf(w * r, w * r, s[0]); s[1] = fmaf(r, r, s[1]);
+        } else {
+            const int lb = p, ub = p + NB;
+            const float dv = u[lb] - u[ub], dx = ux[lb] - ux[ub];
+            bu[lb] = 2.f * dv / (float)NB; bu[ub] = -2.f * dv / (float)NB;
+            bx[lb] = 2.f * dx / (float)NB; bx[ub] = -2.f * dx / (float)NB;
+            bt[lb] = bt[ub] = 0.f; bxx[lb] = bxx[ub] = 0.f;
+            s[2] = fmaf(dv, dv, s[2]); s[3] = fmaf(dx, dx, s[3]);
+        }
+    }
+    __shared__ float red[SA_LOSS_THREADS / 32][SA_NSUM];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < SA_NSUM; ++k) {
+        float v = s[k];
+        for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) red[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < SA_NSUM) {
+        float v = 0.f;
+        for (int w = 0; w < SA_LOSS_THREADS / 32; ++w) v += red[w][threadIdx.x];
+        partial[blockIdx.x * SA_NSUM + threadIdx.x] = v;
+    }
+}
+
+// fixed-order final sum -> out4 = (total, mse_u, mse_b, mse_f) as AC_main.py:228-232 returns them
+__global__ void sa_loss_final_kernel(const float *__restrict__ partial, int nblocks, int NR, int NI, int NB, float *__restrict__ out4)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float s[SA_NSUM] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int b = 0; b < nblocks; ++b)
+            for (int k = 0; k < SA_NSUM; ++k) s[k] += partial[b * SA_NSUM + k];
+        const float mse_b = s[2] / (float)NB + s[3] / (float)NB;
+        out4[0] = s[0] / (float)NI + mse_b + s[4] / (float)NR;
+        out4[1] = s[1] / (float)NI;
+        out4[2] = mse_b;
+        out4[3] = s[5] / (float)NR;
+    }
+}
+
+__global__ void sa_output_backward_kernel(const float *__restrict__ Ubar, const float *__restrict__ Wout, long long N, int W, float *__restrict__ G)
+{
+    const long long total = 4 * N * W;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x)
+        G[e] = Ubar[e / W] * Wout[(int)(e % W)];
+}
+
+__global__ void sa_tick_kernel(int *step) { if (threadIdx.x == 0 && blockIdx.x == 0) *step += 1; }
+
+// tf.keras.optimizers.Adam (TF 2.10): lr_t = lr sqrt(1 - b2^t) / (1 - b1^t);  m += (g - m)(1 - b1);  v += (g^2 - v)(1 - b2);
+// p -= lr_t m / (sqrt(v) + eps).  sign = -1 turns the step into gradient ASCENT (AC_main.py:298 applies -grads to the SA weights).
+__global__ void sa_adam_kernel(float *__restrict__ p, float *__restrict__ m, float *__restrict__ v, const float *__restrict__ g, long long n,
+                               const int *__restrict__ step, double lr, double b1, double b2, float eps, float sign)
+{
+    const int t = *step;
+    const float lr_t = (float)(lr * sqrt(1.0 - pow(b2, (double)t)) / (1.0 - pow(b1, (double)t)));
+    const float omb1 = (float)(1.0 - b1), omb2 = (float)(1.0 - b2);
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const float gg = sign * g[e];
+        const float mm = m[e] + (gg - m[e]) * omb1;
+        const float vv = v[e] + (gg * gg - v[e]) * omb2;
+        m[e] = mm; v[e] = vv;
+        p[e] = p[e] - lr_t * mm / (sqrtf(vv) + eps);
+    }
+}
+
+static inline unsigned blocks_for(long long n, int threads)
+{
+    long long b = (n + threads - 1) / threads;
+    const long long cap = 148LL * 16;
+    return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace gp
+
+using namespace gp;
+
+#define SA_CHECK(cond, msg) do { if (!(cond)) return GPTPINN_E_INVALID; } while (0)
+#define SA_LAUNCHED() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return GPTPINN_E_CUDA; } while (0)
+
+extern "C" int gptpinn_sa_layer0(const float *xt_dev, long long N, const float *W0_dev, const float *b0_dev, int W, float *Z_dev, void *stream)
+{
+    SA_CHECK(xt_dev && W0_dev && b0_dev && Z_dev && N > 0 && W > 0, "gptpinn_sa_layer0");
+    sa_layer0_kernel<<<blocks_for(N * W, 256), 256, 0, (cudaStream_t)stream>>>(xt_dev, W0_dev, b0_dev, N, W, Z_dev);
+    SA_LAUNCHED();
+    return GPTPINN_OK;
+}
+
+extern "C" int gptpinn_sa_act_forward(float *Z_dev, const float *bias_dev, float *A_dev, long long N, int W, void *stream)
+{
+    SA_CHECK(Z_dev && A_dev && N > 0 && W > 0, "gptpinn_sa_act_forward");
+    sa_act_forward_kernel<<<blocks_for(N * W, 256), 256, 0, (cudaStream_t)stream>>>(Z_dev, bias_dev, A_dev, N, W);
+    SA_LAUNCHED();
+    return GPTPINN_OK;
+}
+
+extern "C" int gptpinn_sa_act_backward(const float *Z_dev, float *G_dev, long long N, int W, void *stream)
+{
+    SA_CHECK(Z_dev && G_dev && N > 0 && W > 0, "gptpinn_sa_act_backward");
+    sa_act_backward_kernel<<<blocks_for(N * W, 256), 256, 0, (cudaStream_t)stream>>>(Z_dev, G_dev, N, W);
+    SA_LAUNCHED();
+    return GPTPINN_OK;
+}
+
+extern "C" int gptpinn_sa_output_forward(const float *A_dev, const float *Wout_dev, const float *bout_dev, long long N, int W, float *U_dev, void *stream)
+{
+    SA_CHECK(A_dev && Wout_dev && bout_dev && U_dev && N > 0 && W > 0, "gptpinn_sa_output_forward");
+    sa_output_forward_kernel<<<blocks_for(4 * N * 32, 256), 256, 0, (cudaStream_t)stream>>>(A_dev, Wout_dev, bout_dev, N, W, U_dev);
+    SA_LAUNCHED();
+    return GPTPINN_OK;
+}
+
+extern "C" int gptpinn_sa_loss_workspace_floats(void) { return SA_LOSS_BLOCKS * SA_NSUM; }
+
+extern "C" int gptpinn_sa_loss(const float *U_dev, int NR, int NI, int NB, const float *u0_dev, const float *wf_dev, const float *wu_dev,
+                               double lambda, double eps, float *Ubar_dev, float *gwf_dev, float *gwu_dev, float *loss4_dev,
+                               float *workspace_dev, void *stream)
+{
+    SA_CHECK(U_dev && u0_dev && wf_dev && wu_dev && Ubar_dev && gwf_dev && gwu_dev && loss4_dev && workspace_dev, "gptpinn_sa_loss");
+    SA_CHECK(NR > 0 && NI > 0 && NB > 0, "gptpinn_sa_loss sizes");
+    const long long N = (long long)NR + NI + 2LL * NB;
+    sa_loss_kernel<<<SA_LOSS_BLOCKS, SA_LOSS_THREADS, 0, (cudaStream_t)stream>>>(U_dev, N, NR, NI, NB, u0_dev, wf_dev, wu_dev, (float)lambda, (float)eps,
+                                                                                Ubar_dev, gwf_dev, gwu_dev, workspace_dev);
+    SA_LAUNCHED();
+    sa_loss_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(workspace_dev, SA_LOSS_BLOCKS, NR, NI, NB, loss4_dev);
+    SA_LAUNCHED();
+    return GPTPINN_OK;
+}
+
+extern "C" int gptpinn_sa_output_backward(const float *Ubar_dev, const float *Wout_dev, long long N, int W, float *G_dev, void *stream)
+{
+    SA_CHECK(Ubar_dev && Wout_dev && G_dev && N > 0 && W > 0, "gptpinn_sa_output_backward");
+    sa_output_backward_kernel<<<blocks_for(4 * N * W, 256), 256, 0, (cudaStream_t)stream>>>(Ubar_dev, Wout_dev, N, W, G_dev);
+    SA_LAUNCHED();
+    return GPTPINN_OK;
+}
+
+extern "C" int gptpinn_sa_tick(int *step_dev, void *stream)
+{
+    SA_CHECK(step_dev, "gptpinn_sa_tick");
+    sa_tick_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step_dev);
+    SA_LAUNCHED();
+    return GPTPINN_OK;
+}
+
+extern "C" int gptpinn_sa_adam(float *p_dev, float *m_dev, float *v_dev, const float *g_dev, long long n, const int *step_dev,
+                               double lr, double beta1, double beta2, double eps, int ascent, void *stream)
+{
+    SA_CHECK(p_dev && m_dev && v_dev && g_dev && step_dev && n > 0, "gptpinn_sa_adam");
+    sa_adam_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p_dev, m_dev, v_dev, g_dev, n, step_dev, lr, beta1, beta2,
+                                                                       (float)eps, ascent ? -1.f : 1.f);
+    SA_LAUNCHED();
+    return GPTPINN_OK;
+}

@@ -1,0 +1,323 @@
+"""Self-adaptive PINN trainer for Allen-Cahn without TensorFlow.
+
+Reference: the TensorFlow / Keras code in Allen-Cahn/AC_main.py:204-339 (= AC_SA_test.py:109-245) and the fixed-step
+L-BFGS of eager_lbfgs.py:14-200.  What is reproduced, statement by statement:
+  * network   tanh MLP `layers` ([2,128,128,128,128,1]), Glorot-normal weights (truncated normal, seeded), zero biases;
+  * loss      mean((w_u (u0 - u(x,0)))^2) + mean((u_lb - u_ub)^2) + mean((u_x,lb - u_x,ub)^2) + mean((w_f f)^2),
+              f = u_t - lambda u_xx + eps u^3 - eps u with the true u_xx (AC_main.py:215-244);
+  * fit       `tf_iter` Adam steps (lr 5e-3, beta_1 0.99, Keras epsilon 1e-7) on the weights with SIMULTANEOUS gradient
+              ASCENT Adam steps on the self-adaptive weights w_f [N_f,1] ~ U(0,1), w_u [N_0,1] ~ 100 U(0,1)
+              (AC_main.py:282-298), then up to `newton_iter` L-BFGS iterations (step 0.8, history 50, no line search) on
+              the weights only.
+How it runs on the B200: all points go through the network as one batch with four channels (u, u_x, u_t, u_xx) in
+[4][N][W] tensors; activation maps, their hand-derived adjoints, the loss / seed computation and the Adam updates are the
+CUDA kernels of csrc/sa_pinn.cu (C ABI gptpinn_sa_*); the hidden->hidden maps and the weight-gradient contractions are
+plain fp32 library GEMMs ([4N x W] x [W x W], torch.mm -> cuBLAS).  One whole Adam iteration (forward, reverse, three
+optimizer steps) is captured once into a CUDA graph and replayed: no Python, no allocation, no host sync per step; the
+iteration counter of the bias correction lives on the device.  L-BFGS keeps its history on the device and synchronises
+once per iteration for the reference's scalar tests.  No TensorFlow, no autograd, no CPU path.
+Parity: TensorFlow is not in this image, so trajectories are statistical only; the loss and every gradient are held to an
+fp64 autograd restatement of the same loss in tests/ (oracle/sa_pinn_ref.py).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class CudaOps:
+    """The gptpinn_sa_* kernels on the current torch stream."""
+
+    def __init__(self, device):
+        self.dev = device
+        L = _lib.lib()
+        self.L = L
+        self.ws = torch.zeros(int(L.gptpinn_sa_loss_workspace_floats()), dtype=torch.float32, device=device)
+
+    def _s(self):
+        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr())
+
+    def layer0(self, xt, W0, b0, Z):
+        _lib.check(self.L.gptpinn_sa_layer0(self._p(xt), C.c_longlong(xt.shape[0]), self._p(W0), self._p(b0), C.c_int(W0.shape[0]),
+                                            self._p(Z), self._s()), "gptpinn_sa_layer0")
+
+    def act_forward(self, Z, bias, A):
+        _lib.check(self.L.gptpinn_sa_act_forward(self._p(Z), self._p(bias) if bias is not None else None, self._p(A),
+                                                 C.c_longlong(Z.shape[1]), C.c_int(Z.shape[2]), self._s()), "gptpinn_sa_act_forward")
+
+    def act_backward(self, Z, G):
+        _lib.check(self.L.gptpinn_sa_act_backward(self._p(Z), self._p(G), C.c_longlong(Z.shape[1]), C.c_int(Z.shape[2]), self._s()),
+                   "gptpinn_sa_act_backward")
+
+    def output_forward(self, A, Wout, bout, U):
+        _lib.check(self.L.gptpinn_sa_output_forward(self._p(A), self._p(Wout), self._p(bout), C.c_longlong(A.shape[1]), C.c_int(A.shape[2]),
+                                                    self._p(U), self._s()), "gptpinn_sa_output_forward")
+
+    def loss(self, U, NR, NI, NB, u0, wf, wu, lam, eps, Ubar, gwf, gwu, out4):
+        _lib.check(self.L.gptpinn_sa_loss(self._p(U), C.c_int(NR), C.c_int(NI), C.c_int(NB), self._p(u0), self._p(wf), self._p(wu),
+                                          C.c_double(lam), C.c_double(eps), self._p(Ubar), self._p(gwf), self._p(gwu), self._p(out4),
+                                          self._p(self.ws), self._s()), "gptpinn_sa_loss")
+
+    def output_backward(self, Ubar, Wout, G):
+        _lib.check(self.L.gptpinn_sa_output_backward(self._p(Ubar), self._p(Wout), C.c_longlong(G.shape[1]), C.c_int(G.shape[2]), self._p(G),
+                                                     self._s()), "gptpinn_sa_output_backward")
+
+    def tick(self, step):
+        _lib.check(self.L.gptpinn_sa_tick(self._p(step), self._s()), "gptpinn_sa_tick")
+
+    def adam(self, p, m, v, g, step, lr, beta1, beta2, eps, sign):
+        _lib.check(self.L.gptpinn_sa_adam(self._p(p), self._p(m), self._p(v), self._p(g), C.c_longlong(p.numel()), self._p(step),
+                                          C.c_double(lr), C.c_double(beta1), C.c_double(beta2), C.c_double(eps), C.c_int(1 if sign < 0 else 0),
+                                          self._s()), "gptpinn_sa_adam")
+
+
+def glorot_normal(fan_out, fan_in, generator):
+    """Keras GlorotNormal: truncated normal (|z| <= 2) with stddev sqrt(2 / (fan_in + fan_out)) / 0.87962566103423978."""
+    std = math.sqrt(2.0 / (fan_in + fan_out)) / 0.87962566103423978
+    w = torch.empty(fan_out, fan_in)
+    torch.nn.init.trunc_normal_(w, mean=0.0, std=1.0, a=-2.0, b=2.0, generator=generator)
+    return (w * std).float()
+
+
+class SAPinn:
+    """One self-adaptive PINN: network weights + self-adaptive weights + everything fit() needs, resident on the device."""
+
+    def __init__(self, layers, xt_f, xt0, u0, xt_lb, xt_ub, lmbda, eps, col_weights=None, u_weights=None, seed=0, ops=None,
+                 dtype=torch.float32):
+        dev = xt_f.device
+        if ops is None:
+            if dev.type != "cuda":
+                raise _lib.GptPinnError("SAPinn: tensors must live on the GPU (no CPU path)")
+            ops = CudaOps(dev)
+        self.ops, self.dev, self.dtype = ops, dev, dtype
+        self.layers = [int(x) for x in layers]
+        hidden = self.layers[1:-1]
+        if self.layers[0] != 2 or self.layers[-1] != 1 or len(hidden) < 1 or len(set(hidden)) != 1:
+            raise ValueError("SAPinn needs a [2, W, ..., W, 1] network")
+        self.W, self.NH = hidden[0], len(hidden)
+        self.lmbda, self.eps = float(lmbda), float(eps)
+        self.NR, self.NI, self.NB = xt_f.shape[0], xt0.shape[0], xt_lb.shape[0]
+        if xt_ub.shape[0] != self.NB:
+            raise ValueError("lower and upper boundary sets must pair up")
+        self.N = self.NR + self.NI + 2 * self.NB
+        f = lambda t: t.detach().to(dev, dtype).contiguous()
+        self.xt = torch.cat((f(xt_f), f(xt0), f(xt_lb), f(xt_ub)), 0).contiguous()
+        self.u0 = f(u0).reshape(-1)
+        g = torch.Generator().manual_seed(seed)
+        # AC_main.py:347-348: col_weights ~ U(0,1) [N_f,1], u_weights ~ 100 U(0,1) [N0,1]
+        self.wf = f(col_weights).reshape(-1).clone() if col_weights is not None else torch.rand(self.NR, generator=g).to(dev, dtype)
+        self.wu = f(u_weights).reshape(-1).clone() if u_weights is not None else (100.0 * torch.rand(self.NI, generator=g)).to(dev, dtype)
+        # flat parameter vector: per layer W (nn.Linear layout [out][in], row-major) then b
+        sizes = []
+        for fi, fo in zip(self.layers[:-1], self.layers[1:]):
+            sizes += [fo * fi, fo]
+        self.P = sum(sizes)
+        self.theta = torch.zeros(self.P, dtype=dtype, device=dev)
+        self.grad = torch.zeros(self.P, dtype=dtype, device=dev)
+        self.Wv, self.bv, self.gW, self.gb = [], [], [], []
+        off = 0
+        for fi, fo in zip(self.layers[:-1], self.layers[1:]):
+            self.Wv.append(self.theta[off:off + fo * fi].view(fo, fi)); self.gW.append(self.grad[off:off + fo * fi].view(fo, fi)); off += fo * fi
+            self.bv.append(self.theta[off:off + fo]); self.gb.append(self.grad[off:off + fo]); off += fo
+        for Wl in self.Wv:
+            Wl.copy_(glorot_normal(Wl.shape[0], Wl.shape[1], g).to(dev, dtype))
+        # workspaces (allocated once: an iteration never allocates, so it can live in a CUDA graph)
+        N, W = self.N, self.W
+        z = lambda *s: torch.zeros(*s, dtype=dtype, device=dev)
+        self.Z = [z(4, N, W) for _ in range(self.NH)]
+        self.A = [z(4, N, W) for _ in range(self.NH)]
+        self.G = z(4, N, W)
+        self.G2 = z(4, N, W)
+        self.U, self.Ubar = z(4, N), z(4, N)
+        self.gwf, self.gwu = z(self.NR), z(self.NI)
+        self.loss4 = z(4)
+        self.tmpW = z(W)
+        self.step = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.m_t, self.v_t = z(self.P), z(self.P)
+        self.m_f, self.v_f = z(self.NR), z(self.NR)
+        self.m_u, self.v_u = z(self.NI), z(self.NI)
+        self._graph = None
+
+    # ------------------------------------------------------------------ loss and gradients
+    def loss_and_grad(self):
+        """Fills self.loss4 = (total, mse_u, mse_b, mse_f), self.grad (flat, d total / d weights), self.gwf, self.gwu."""
+        o, N, W, NH = self.ops, self.N, self.W, self.NH
+        o.layer0(self.xt, self.Wv[0], self.bv[0], self.Z[0])
+        for l in range(NH):
+            o.act_forward(self.Z[l], None if l == 0 else self.bv[l], self.A[l])
+            if l < NH - 1:
+                torch.mm(self.A[l].view(4 * N, W), self.Wv[l + 1].t(), out=self.Z[l + 1].view(4 * N, W))
+        o.output_forward(self.A[NH - 1], self.Wv[NH], self.bv[NH], self.U)
+        o.loss(self.U, self.NR, self.NI, self.NB, self.u0, self.wf, self.wu, self.lmbda, self.eps, self.Ubar, self.gwf, self.gwu, self.loss4)
+        # reverse
+        torch.mm(self.Ubar.view(1, 4 * N), self.A[NH - 1].view(4 * N, W), out=self.gW[NH])
+        torch.sum(self.Ubar[0], dim=0, keepdim=True, out=self.gb[NH])
+        G, G2 = self.G, self.G2
+        o.output_backward(self.Ubar, self.Wv[NH], G)
+        for l in range(NH - 1, -1, -1):
+            o.act_backward(self.Z[l], G)
+            torch.sum(G[0], dim=0, out=self.gb[l])
+            if l > 0:
+                torch.mm(G.view(4 * N, W).t(), self.A[l - 1].view(4 * N, W), out=self.gW[l])
+                torch.mm(G.view(4 * N, W), self.Wv[l], out=G2.view(4 * N, W))
+                G, G2 = G2, G
+            else:
+                # first map: inputs (x, t) with channels (x,1,0,0) and (t,0,1,0)
+                torch.mv(G[0].t(), self.xt[:, 0], out=self.tmpW)
+                torch.add(self.tmpW, torch.sum(G[1], dim=0), out=self.gW[0][:, 0])
+                torch.mv(G[0].t(), self.xt[:, 1], out=self.tmpW)
+                torch.add(self.tmpW, torch.sum(G[2], dim=0), out=self.gW[0][:, 1])
+        return self.loss4
+
+    # ------------------------------------------------------------------ Adam phase (AC_main.py:282-298)
+    def _adam_iteration(self, lr, beta1):
+        self.loss_and_grad()
+        self.ops.tick(self.step)
+        self.ops.adam(self.theta, self.m_t, self.v_t, self.grad, self.step, lr, beta1, 0.999, 1e-7, +1)
+        self.ops.adam(self.wf, self.m_f, self.v_f, self.gwf, self.step, lr, beta1, 0.999, 1e-7, -1)
+        self.ops.adam(self.wu, self.m_u, self.v_u, self.gwu, self.step, lr, beta1, 0.999, 1e-7, -1)
+
+    def adam_fit(self, iters, lr=0.005, beta1=0.99, record=False, use_graph=True, verbose=False):
+        """`iters` simultaneous steps: Adam descent on the weights, Adam ascent on w_f and w_u.  Returns the recorded
+        total losses (device tensor [iters]) when record, else None."""
+        rec = torch.zeros(max(iters, 1), dtype=self.dtype, device=self.dev) if record else None
+
+        def after(it):
+            if record:
+                rec[it] = self.loss4[0]
+            if verbose and (it % 1000 == 0 or it == iters - 1):
+                l4 = self.loss4.tolist()
+                print(f"Epoch: {it}\nmse_0: {l4[1]} | mse_b: {l4[2]} | mse_f: {l4[3]} | Total Loss: {l4[0]}\n")
+
+        it, graph = 0, None
+        if use_graph and self.dev.type == "cuda" and iters > 8:
+            # two real iterations on a side stream first (cuBLAS workspaces, lazy initialisation), then ONE iteration is
+            # captured (capturing does not execute it) and replayed for the rest of the phase
+            side = torch.cuda.Stream(self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._adam_iteration(lr, beta1)
+                    after(it)
+                    it += 1
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._adam_iteration(lr, beta1)
+        while it < iters:
+            if graph is not None:
+                graph.replay()
+            else:
+                self._adam_iteration(lr, beta1)
+            after(it)
+            it += 1
+        return rec
+
+    # ------------------------------------------------------------------ L-BFGS phase (eager_lbfgs.py:14-200)
+    def lbfgs_fit(self, max_iter, learning_rate=0.8, history=50, record=False, verbose=False):
+        """Fixed-step L-BFGS on the network weights (w_f, w_u frozen), literal two-loop recursion with the reference's
+        stopping tests.  Returns the list of losses (f_hist) when record."""
+        tolFun, tolX = 1e-5, 1e-9
+        x = self.theta
+        S = torch.zeros(history, self.P, dtype=self.dtype, device=self.dev)       # old_dirs
+        Y = torch.zeros(history, self.P, dtype=self.dtype, device=self.dev)       # old_stps
+        ro = torch.zeros(history, dtype=self.dtype, device=self.dev)
+        k = 0
+        Hdiag = 1.0
+        f_hist = []
+        if max_iter <= 0:
+            return f_hist
+        self.loss_and_grad()
+        g = self.grad.clone()
+        f, gsum = torch.stack((self.loss4[0], g.abs().sum())).tolist()
+        f_hist.append(f)
+        evals = 1
+        if gsum <= tolFun:
+            return f_hist
+        d = t = g_old = None
+        n_iter = 0
+        while n_iter < max_iter:
+            n_iter += 1
+            if n_iter == 1:
+                d = -g
+            else:
+                y = g - g_old
+                s = d * t
+                ys, yy = torch.stack((torch.dot(y, s), torch.dot(y, y))).tolist()          # host sync 1 of 2
+                if ys > 1e-10:
+                    if k == history:                      # shift the history by one (limited memory)
+                        S = torch.roll(S, -1, 0); Y = torch.roll(Y, -1, 0); ro = torch.roll(ro, -1, 0)
+                        k -= 1
+                    S[k].copy_(s); Y[k].copy_(y)
+                    ro[k] = 1.0 / ys
+                    k += 1
+                    Hdiag = ys / yy
+                # two-loop recursion entirely on the device (the scalars al_i, be_i stay 0-dim tensors)
+                al = [None] * k
+                q = -g
+                for i in range(k - 1, -1, -1):
+                    al[i] = torch.dot(S[i], q) * ro[i]
+                    q = q - al[i] * Y[i]
+                r = q * Hdiag
+                for i in range(k):
+                    be_i = torch.dot(Y[i], r) * ro[i]
+                    r = r + (al[i] - be_i) * S[i]
+                d = r
+            g_old = g
+            gtd = torch.dot(g, d)
+            dsum = d.abs().sum()
+            if n_iter == 1:
+                gtd_h, dsum_h = torch.stack((gtd, dsum)).tolist()
+                t = min(1.0, 1.0 / gsum)
+            else:
+                gtd_h, dsum_h = torch.stack((gtd, dsum)).tolist()                         # host sync 2 of 2
+                t = learning_rate
+            if gtd_h > -tolX:
+                break
+            x.add_(d, alpha=t)
+            if n_iter != max_iter:
+                self.loss_and_grad()
+                g = self.grad.clone()
+                f, gsum = torch.stack((self.loss4[0], g.abs().sum())).tolist()
+            evals += 1
+            f_hist.append(f)
+            if verbose and (n_iter % 1000 == 0 or n_iter == max_iter):
+                print("Epoch: %3d | Loss: %6.5f " % (n_iter, f))
+            if n_iter == max_iter or evals >= max_iter * 1.25:
+                break
+            if gsum <= tolFun:
+                break
+            if dsum_h * abs(t) <= tolX:
+                break
+            if abs(f) < tolX:                 # eager_lbfgs.py:171 `tf.abs(f, f_old) < tolX` == |f| < tolX
+                break
+        return f_hist
+
+    def fit(self, tf_iter, newton_iter, lr_adam=0.005, lr_lbfgs=0.8, record=False, verbose=True):
+        """AC_main.py:275-338 `fit`."""
+        if verbose:
+            print("Starting ADAM training")
+        a = self.adam_fit(tf_iter, lr=lr_adam, record=record, verbose=verbose)
+        if verbose:
+            print("Starting L-BFGS training")
+        b = self.lbfgs_fit(newton_iter, learning_rate=lr_lbfgs, record=record, verbose=verbose)
+        return (a.cpu().numpy() if a is not None else None), np.asarray(b)
+
+    # ------------------------------------------------------------------ hand-over to the GPT-PINN side
+    def weights_for_P(self):
+        """(SA_w, SA_b) exactly as AC_main.py:371-376 builds them for AC_models.P: torch [out, in] weights, [out] biases."""
+        return [w.detach().clone() for w in self.Wv], [b.detach().clone() for b in self.bv]
+
+    def predict(self, xt):
+        """u at arbitrary points (AC_main.py:331-334 `predict`), through the same kernels."""
+        from . import precomp
+        u = torch.empty(xt.shape[0], dtype=torch.float32, device=self.dev)
+        precomp.mlp_channels(list(zip(self.Wv, self.bv)), "tanh", xt.to(self.dev, torch.float32), v=u)
+        return u

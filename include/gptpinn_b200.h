@@ -232,6 +232,37 @@ int  gptpinn_pinn_train(gptpinn_handle *h, const gptpinn_pinn_problem *prob, con
 int  gptpinn_pinn_train_batch(gptpinn_handle *h, int nbatch, const gptpinn_pinn_problem *probs, const gptpinn_mlp *nets,
                               const gptpinn_train_args *args, float *status_dev, void *stream);
 
+/* ---- self-adaptive PINN for Allen-Cahn: device kernels of the TensorFlow-free trainer ------------------------------
+ * Replaces the TensorFlow graph of Allen-Cahn/AC_main.py:204-339 (= AC_SA_test.py:109-245): neural_net / loss / f_model /
+ * u_x_model / grad and the two Adam optimizers of fit().  The four channels (u, u_x, u_t, u_xx -- the TRUE second
+ * x-derivative, AC_main.py:235-244) of a tanh MLP are propagated in closed form and the reverse pass is hand-derived; all
+ * points (collocation NR, initial NI, lower boundary NB, upper boundary NB, in that order) run as one batch of
+ * N = NR + NI + 2 NB points.  Activations, pre-activations and adjoints are [4][N][W] fp32 device tensors (channel-major,
+ * W = hidden width), so a hidden->hidden map of all channels is ONE [4N x W] x [W x W] GEMM, which the host side
+ * (gptpinn/sa_pinn.py) issues as a plain library GEMM; every other step is one of the calls below.                      */
+/* Z[c][p][j]: pre-activations of the first hidden layer from the points xt[N][2] (W0 is nn.Linear layout [W][2])          */
+int  gptpinn_sa_layer0(const float *xt_dev, long long N, const float *W0_dev, const float *b0_dev, int W, float *Z_dev, void *stream);
+/* Z[0] += bias (NULL: none; stored back), A = tanh channels of Z                                                            */
+int  gptpinn_sa_act_forward(float *Z_dev, const float *bias_dev, float *A_dev, long long N, int W, void *stream);
+/* G: adjoint of the activations on entry, adjoint of the pre-activations on return (in place)                             */
+int  gptpinn_sa_act_backward(const float *Z_dev, float *G_dev, long long N, int W, void *stream);
+/* U[c][p] = A[c][p][:] . Wout (+ bout on channel 0)                                                                         */
+int  gptpinn_sa_output_forward(const float *A_dev, const float *Wout_dev, const float *bout_dev, long long N, int W, float *U_dev, void *stream);
+/* loss of AC_main.py:215-232 from U[4][N]: loss4 = (total, mse_u, mse_b, mse_f); Ubar = dL/dU; gwf / gwu = dL/d(col_weights),
+ * dL/d(u_weights) (the ascent directions of AC_main.py:298).  workspace: gptpinn_sa_loss_workspace_floats() floats.          */
+int  gptpinn_sa_loss_workspace_floats(void);
+int  gptpinn_sa_loss(const float *U_dev, int NR, int NI, int NB, const float *u0_dev, const float *wf_dev, const float *wu_dev,
+                     double lambda, double eps, float *Ubar_dev, float *gwf_dev, float *gwu_dev, float *loss4_dev,
+                     float *workspace_dev, void *stream);
+/* G[c][p][j] = Ubar[c][p] * Wout[j]: adjoint of the last hidden layer's activations                                         */
+int  gptpinn_sa_output_backward(const float *Ubar_dev, const float *Wout_dev, long long N, int W, float *G_dev, void *stream);
+/* *step_dev += 1 (the optimizer's iteration counter lives on the device so that a whole Adam iteration is one CUDA graph)  */
+int  gptpinn_sa_tick(int *step_dev, void *stream);
+/* tf.keras.optimizers.Adam step (TF 2.10 semantics, AC_main.py:282-283: lr 5e-3, beta_1 0.99, epsilon 1e-7) on a flat
+ * vector; ascent != 0 applies it to -g (gradient ASCENT on the self-adaptive weights, AC_main.py:298).                      */
+int  gptpinn_sa_adam(float *p_dev, float *m_dev, float *v_dev, const float *g_dev, long long n, const int *step_dev,
+                     double lr, double beta1, double beta2, double eps, int ascent, void *stream);
+
 /* Host-only (no CUDA call): the work-item plan gptpinn_kg_sweep would build for this grid on a device
  * with n_sm SMs.  sl_hist[l] = number of items with 2^l sibling lanes; *covered = parameters assigned
  * (must equal Np).  Used by tests and for tuning; no reference counterpart.                            */

@@ -98,7 +98,7 @@ def test_kg_inputs_fills_columns():
         assert views[3].data_ptr() == buf["out_IC_t"].data_ptr()      # order: out, xx, tt, IC_t, IC, BC
     for k in names:
         got, want = buf[k][:, :3].cpu().numpy(), g[k][:, :3]
-        assert np.max(np.abs(got - want)) <= 2e-5 * np.max(np.abs(want)), k
+        assert np.max(np.abs(got - want)) <= 1e-5 * np.max(np.abs(want)), k
         if k != "out_test":
             assert (buf[k][:, 3:] == 1).all()
 
@@ -146,7 +146,7 @@ def test_burgers_dropin():
         assert set(idx_list[i].tolist()) == set(g["idx_list"][i].tolist())
     for k in names:
         got, want = buf[k][:, :2].cpu().numpy(), g[k][:, :2]
-        assert np.max(np.abs(got - want)) <= 2e-5 * np.max(np.abs(want)), k
+        assert np.max(np.abs(got - want)) <= 1e-5 * np.max(np.abs(want)), k
 
 
 def test_allen_cahn_dropin():

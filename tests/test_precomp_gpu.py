@@ -6,7 +6,7 @@ import torch
 from conftest import load_golden
 
 pytestmark = pytest.mark.gpu
-PRE_TOL = 2e-5
+PRE_TOL = 1e-5          # of the column's max-abs; fp64 adjudication in test_round2_gpu.py
 
 
 def _col_err(a, b):
@@ -63,7 +63,7 @@ def test_burgers_and_ac_channels_vs_oracle_and_golden():
     ch = _eval(L, "tanh", g["xt_resid"], "vtq")
     assert _col_err(ch["v"], g["out"][:, 1]) < PRE_TOL
     assert _col_err(ch["t"], g["out_t"][:, 1]) < PRE_TOL
-    assert _col_err(ch["q"], g["out_xx"][:, 1]) < 5 * PRE_TOL
+    assert _col_err(ch["q"], g["out_xx"][:, 1]) < PRE_TOL
     ub = _eval(L, "tanh", g["BC_xt_ub"], "vx")
     assert _col_err(ub["x"], g["out_BC_ub_x"][:, 1]) < PRE_TOL
 
