@@ -47,11 +47,10 @@ def latin_hypercube(n, dims, rng):
 
 
 def find_mat(path):
-    for cand in (path, os.path.join(os.getcwd(), "AC.mat"), os.path.join(HERE, "AC.mat"),
-                 os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle", "_ref", "Allen-Cahn", "AC.mat")):
+    for cand in (path, os.environ.get("GPTPINN_AC_MAT"), os.path.join(os.getcwd(), "AC.mat"), os.path.join(HERE, "AC.mat")):
         if cand and os.path.exists(cand):
             return cand
-    raise SystemExit("AC.mat not found (the reference ships it in Allen-Cahn/AC.mat): pass --mat")
+    raise SystemExit("AC.mat not found (the reference ships it as Allen-Cahn/AC.mat): pass --mat or set GPTPINN_AC_MAT")
 
 
 def main(argv=None):

@@ -17,7 +17,7 @@ optimizer steps) is captured once into a CUDA graph and replayed: no Python, no 
 iteration counter of the bias correction lives on the device.  L-BFGS keeps its history on the device and synchronises
 once per iteration for the reference's scalar tests.  No TensorFlow, no autograd, no CPU path.
 Parity: TensorFlow is not in this image, so trajectories are statistical only; the loss and every gradient are held to an
-fp64 autograd restatement of the same loss in tests/ (oracle/sa_pinn_ref.py).
+fp64 autograd restatement of the same loss in the test suite (tests/test_sa_pinn.py).
 """
 import ctypes as C
 import math
