@@ -15,6 +15,7 @@
 #include "precomp.cuh"
 #include "pinn_train.cuh"
 #include "sweep_kernel.cuh"
+#include "sweep_rows.cuh"
 
 namespace gp {
 #define GP_DECL(P, N) cudaError_t sweep_launch_##P##_##N(const SweepParams &, int, int, int, size_t, cudaStream_t);
@@ -26,6 +27,15 @@ static const sweep_launch_fn kLaunch[3][15] = {
     {GP_ROW9(0), sweep_launch_0_10, sweep_launch_0_11, sweep_launch_0_12, sweep_launch_0_13, sweep_launch_0_14, sweep_launch_0_15},
     {GP_ROW9(1), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr},
     {GP_ROW9(2), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}};
+#define GP_RDECL(P, N) cudaError_t sweep_rows_launch_##P##_##N(const RowsParams &, int, size_t, cudaStream_t);
+#define GP_RDECL_ALL(P) GP_RDECL(P, 1) GP_RDECL(P, 2) GP_RDECL(P, 3) GP_RDECL(P, 4) GP_RDECL(P, 5) GP_RDECL(P, 6) GP_RDECL(P, 7) GP_RDECL(P, 8) GP_RDECL(P, 9)
+GP_RDECL_ALL(0) GP_RDECL_ALL(1) GP_RDECL_ALL(2)
+GP_RDECL(0, 10) GP_RDECL(0, 11) GP_RDECL(0, 12) GP_RDECL(0, 13) GP_RDECL(0, 14) GP_RDECL(0, 15)
+#define GP_RROW9(P) sweep_rows_launch_##P##_1, sweep_rows_launch_##P##_2, sweep_rows_launch_##P##_3, sweep_rows_launch_##P##_4, sweep_rows_launch_##P##_5, sweep_rows_launch_##P##_6, sweep_rows_launch_##P##_7, sweep_rows_launch_##P##_8, sweep_rows_launch_##P##_9
+static const rows_launch_fn kRowsLaunch[3][15] = {
+    {GP_RROW9(0), sweep_rows_launch_0_10, sweep_rows_launch_0_11, sweep_rows_launch_0_12, sweep_rows_launch_0_13, sweep_rows_launch_0_14, sweep_rows_launch_0_15},
+    {GP_RROW9(1), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr},
+    {GP_RROW9(2), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}};
 static const int kMaxN[3] = {15, 9, 9};
 }  // namespace gp
 
@@ -54,6 +64,7 @@ struct gptpinn_handle {
     void *sibs = nullptr;      size_t sibs_cap = 0;       // bytes
     unsigned int *counter = nullptr;                      // work-item ticket
     void *train_ws = nullptr;  size_t train_cap = 0;      // packed params | adam m | adam v | partials | status | stop
+    void *rows_ws = nullptr;   size_t rows_cap = 0;       // row-partitioned sweep: parameter table | coefficients | CTA partials
 };
 
 static int ensure(void **ptr, size_t *cap, size_t need)
@@ -96,6 +107,7 @@ extern "C" int gptpinn_destroy(gptpinn_handle *h)
     if (h->sibs) cudaFree(h->sibs);
     if (h->counter) cudaFree(h->counter);
     if (h->train_ws) cudaFree(h->train_ws);
+    if (h->rows_ws) cudaFree(h->rows_ws);
     delete h;
     return GPTPINN_OK;
 }
@@ -115,6 +127,8 @@ static inline uint64_t key_of(const ParamRow &r)
 
 struct Plan {
     int M = 1, SL = 1, W = 1, ctas = 1, rounds = 1, groups = 0, priv = 0, K = 1;
+    bool rows = false;                                   // row-partitioned kernel (sweep_rows.cuh) instead of work items
+    double cost = 0.0;                                   // modelled SMSP cycles per epoch of the chosen work-item plan
     std::vector<ItemDesc> items;
     std::vector<SibDesc> sibs;
 };
@@ -269,7 +283,7 @@ static int make_plan(std::vector<ParamRow> &rows, int pde, int n, int n_sm, cons
         return fail(GPTPINN_E_INVALID, "cfg_M must be 0, 1, 2, 4 or 5");
     if (a->cfg_SL != 0 && (a->cfg_SL < 1 || a->cfg_SL > 32 || (a->cfg_SL & (a->cfg_SL - 1))))
         return fail(GPTPINN_E_INVALID, "cfg_SL must be 0 or a power of two <= 32");
-    if (a->cfg_mode < 0 || a->cfg_mode > 2) return fail(GPTPINN_E_INVALID, "cfg_mode must be 0, 1 or 2");
+    if (a->cfg_mode < 0 || a->cfg_mode > 3) return fail(GPTPINN_E_INVALID, "cfg_mode must be 0, 1, 2 or 3");
 
     if (a->cfg_K != 0 && !(a->cfg_K == 1 || a->cfg_K == 2 || a->cfg_K == 4 || a->cfg_K == 8))
         return fail(GPTPINN_E_INVALID, "cfg_K must be 0, 1, 2, 4 or 8");
@@ -360,6 +374,7 @@ static int make_plan(std::vector<ParamRow> &rows, int pde, int n, int n_sm, cons
         }
     }
     if (bM == 0) return fail(GPTPINN_E_INVALID, "no feasible sweep configuration");
+    plan.cost = best;
     plan.M = bM; plan.SL = bSL; plan.W = std::max(1, bW); plan.priv = bPriv; plan.K = bK;
     if (!bPriv) {
         bestChunks.clear();
@@ -402,6 +417,120 @@ static int make_plan(std::vector<ParamRow> &rows, int pde, int n, int n_sm, cons
 // ------------------------------------------------------------------------------------------
 struct Segments { long long rows[MAX_SEG]; int nseg; };
 
+// ------------------------------------------------------------------------------------------
+// row-partitioned kernel (sweep_rows.cuh): cost model and launch
+// ------------------------------------------------------------------------------------------
+struct RowsGeom { int npsp, rs, chunk_rows; size_t smem; bool ok; };
+
+static RowsGeom rows_geometry(int pde, int n, int Np, const Segments &seg, int G)
+{
+    RowsGeom g = {1, ROWS_THREADS, 0, 0, false};
+    if (Np < 1 || Np > ROWS_MAX_PARAMS) return g;
+    const int nps = (Np + ROWS_M - 1) / ROWS_M;
+    int npsp = 1;
+    while (npsp < nps) npsp <<= 1;
+    g.npsp = npsp; g.rs = ROWS_THREADS / npsp;
+    const int narr = pde == PDE_B ? 4 : 3, nvec = pde == PDE_KG ? 2 : 1, nqx = (n + 3) / 4;
+    const size_t row_floats = (size_t)narr * nqx * 4 + nvec;
+    size_t fl = 0;
+    for (int s = 1; s < seg.nseg; ++s) {
+        long long share = (seg.rows[s] + G - 1) / G + 1;
+        share = std::max<long long>(4, (share + 3) & ~3LL);
+        fl += (size_t)share * row_floats + 4;
+    }
+    if (g.rs > 1) fl += (size_t)ROWS_THREADS * ROWS_M * (n + 1);
+    const size_t budget = (size_t)(220 * 1024) / sizeof(float);
+    if (fl + 64 * row_floats > budget) return g;
+    long long share0 = (seg.rows[0] + G - 1) / G + 1;
+    share0 = std::max<long long>(4, (share0 + 3) & ~3LL);
+    long long cap0 = (long long)((budget - fl) / row_floats) & ~3LL;
+    cap0 = std::min<long long>(cap0, 2048);                              // streaming chunk: no need for more
+    g.chunk_rows = (int)std::min<long long>(share0, cap0);
+    g.smem = (fl + (size_t)g.chunk_rows * row_floats + 8) * sizeof(float);
+    g.ok = true;
+    return g;
+}
+
+// modelled SMSP cycles per epoch, in the units of item_instr(): FMAs of the T-free formulation + row loads, all parameters
+// on every CTA's share of the rows, plus two grid barriers and the partial-sum traffic
+static double rows_cost(int pde, int n, int Np, const Segments &seg, int G, const RowsGeom &g)
+{
+    const double fma_res = (pde == PDE_B ? 8.0 : 6.0) * n + 14.0, fma_icbc = (pde == PDE_KG ? 4.0 : 2.0) * n + 8.0, fma_bc = (pde == PDE_AC ? 3.0 : 2.0) * n + 6.0;
+    double rows_inst = 0.0;
+    for (int s = 0; s < seg.nseg; ++s) {
+        const double share = std::ceil((double)seg.rows[s] / G / g.rs);                      // rows per thread
+        rows_inst += share * ROWS_M * (s == 0 ? fma_res : (s == 1 ? fma_icbc : fma_bc));
+    }
+    const double issue = rows_inst * 2.0 / 0.70;                        // 8 warps = 2 per SMSP, ~70 % issue efficiency
+    const double barriers = 2.0 * 5500.0;                               // two grid barriers, ~2.8 us each at 1.96 GHz
+    const double traffic = 2.0 * (double)Np * (n + 1) * 4.0 * G / kL2BytesPerCycle + (double)G * 30.0;   // partials written + read; G dependent loads
+    return issue + barriers + traffic;
+}
+
+static int run_sweep_rows(gptpinn_handle *h, int pde, int n, const Segments &seg, PackJobs &jobs, bool has_fhat,
+                          int NR, int NI, int NB, const std::vector<ParamRow> &rows, const gptpinn_sweep_args *a,
+                          gptpinn_sweep_info *info, const RowsGeom &geo, int G, cudaStream_t st)
+{
+    const int RT = RT_PRIV;
+    const int slot = pde == PDE_KG ? SlotFloats<PDE_KG, RT_PRIV>::value : (pde == PDE_B ? SlotFloats<PDE_B, RT_PRIV>::value : SlotFloats<PDE_AC, RT_PRIV>::value);
+    RowsParams p;
+    memset(&p, 0, sizeof(p));
+    long long tiles = 0, max_rows = 0, tile0[MAX_SEG];
+    for (int s = 0; s < seg.nseg; ++s) {
+        tile0[s] = tiles;
+        p.seg_rows[s] = (int)seg.rows[s];
+        p.seg_tile0[s] = (int)tiles;
+        tiles += (seg.rows[s] + RT - 1) / RT;
+        max_rows = std::max(max_rows, seg.rows[s]);
+    }
+    for (int i = 0; i < jobs.nmat; ++i) jobs.mat[i].tile0 = tile0[jobs.mat[i].tile0];
+    for (int i = 0; i < jobs.nvec; ++i) jobs.vec[i].tile0 = tile0[jobs.vec[i].tile0];
+    jobs.slot = slot;
+    jobs.rt = RT;
+    size_t cap_f = h->packed_cap * sizeof(float);
+    int rc = ensure((void **)&h->packed, &cap_f, (size_t)tiles * slot * sizeof(float));
+    h->packed_cap = cap_f / sizeof(float);
+    if (rc) return rc;
+    const int Np = a->Np, NV = n + 1;
+    const size_t pp_b = (size_t)Np * sizeof(float4), cg_b = (((size_t)Np * n * sizeof(float)) + 15) & ~(size_t)15;
+    const size_t part_b = (size_t)G * Np * NV * sizeof(float);
+    rc = ensure(&h->rows_ws, &h->rows_cap, pp_b + cg_b + part_b);
+    if (rc) return rc;
+    std::vector<float4> pp((size_t)Np);
+    for (const ParamRow &r : rows) pp[(size_t)r.idx] = make_float4(r.tp0, r.tp1, r.sp0, r.sp1);
+    CUDA_TRY(cudaMemsetAsync(h->packed, 0, (size_t)tiles * slot * sizeof(float), st));
+    CUDA_TRY(launch_pack(jobs, h->packed, max_rows, st));
+    CUDA_TRY(cudaMemcpyAsync(h->rows_ws, pp.data(), pp_b, cudaMemcpyHostToDevice, st));      // pageable source: consumed on return
+    p.packed = h->packed;
+    p.nseg = seg.nseg;
+    p.slot = slot;
+    p.chunk_rows = geo.chunk_rows;
+    p.invR = (float)(1.0 / NR); p.invI = (float)(1.0 / NI); p.invB = (float)(1.0 / NB);
+    p.fac1 = (float)(2.0 / NR); p.fac2 = (float)(2.0 / NB); p.fac3 = (float)(2.0 / NI);
+    p.lr = (float)a->lr;
+    p.epochs = a->epochs;
+    p.rec_every = (a->trace_dev && a->rec_every > 0) ? a->rec_every : 0;
+    p.nrec = p.rec_every > 0 ? a->epochs / p.rec_every + 1 : 0;
+    p.has_fhat = has_fhat ? 1 : 0;
+    p.Np = Np; p.npsp = geo.npsp; p.rs = geo.rs;
+    p.pp = (const float4 *)h->rows_ws;
+    p.c0 = a->c0_dev; p.c0_per_param = a->c0_per_param;
+    p.c_out = a->c_out_dev; p.f_out = a->f_out_dev; p.m_out = a->m_out_dev;
+    p.trace = p.rec_every > 0 ? a->trace_dev : nullptr;
+    p.cglob = (float *)((char *)h->rows_ws + pp_b);
+    p.partial = (float *)((char *)h->rows_ws + pp_b + cg_b);
+    rows_launch_fn fn = kRowsLaunch[pde][n - 1];
+    if (!fn) return fail(GPTPINN_E_UNSUPPORTED, "no row-partitioned kernel compiled for pde=%d n=%d", pde, n);
+    CUDA_TRY(fn(p, G, geo.smem, st));
+    if (info) {
+        memset(info, 0, sizeof(*info));
+        info->M = ROWS_M; info->SL = geo.npsp; info->W = ROWS_THREADS / 32; info->items = Np; info->groups = Np;
+        info->ctas = G; info->rounds = 1; info->priv = 2; info->K = geo.rs; info->kernels_launched = 2;
+        info->smem_bytes = (int)geo.smem; info->tiles_per_pass = (int)tiles;
+    }
+    return GPTPINN_OK;
+}
+
 static int run_sweep(gptpinn_handle *h, int pde, int n, const Segments &seg, PackJobs &jobs, bool has_fhat,
                      int NR, int NI, int NB, std::vector<ParamRow> &rows, const gptpinn_sweep_args *a,
                      gptpinn_sweep_info *info, cudaStream_t st)
@@ -415,6 +544,25 @@ static int run_sweep(gptpinn_handle *h, int pde, int n, const Segments &seg, Pac
     if (a->Np == 0) {
         if (info) memset(info, 0, sizeof(*info));
         return GPTPINN_OK;
+    }
+    // row-partitioned kernel: few parameters (<= 1024), no early-exit bound; chosen by cfg_mode 3 or by the cost model
+    if (a->cfg_mode == 3 || (a->cfg_mode == 0 && !a->bound_dev && a->Np <= ROWS_MAX_PARAMS)) {
+        int coop = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        const RowsGeom geo = rows_geometry(pde, n, a->Np, seg, h->n_sm);
+        if (a->cfg_mode == 3) {
+            if (a->bound_dev) return fail(GPTPINN_E_INVALID, "bound_dev (early exit) is not available in the row-partitioned kernel");
+            if (!coop || !geo.ok) return fail(GPTPINN_E_UNSUPPORTED, "row-partitioned kernel: needs <= %d parameters, cooperative launch and the boundary rows in shared memory", ROWS_MAX_PARAMS);
+            return run_sweep_rows(h, pde, n, seg, jobs, has_fhat, NR, NI, NB, rows, a, info, geo, h->n_sm, st);
+        }
+        if (coop && geo.ok && !a->cfg_M && !a->cfg_SL && !a->cfg_W && !a->cfg_K) {
+            Plan probe;
+            std::vector<ParamRow> tmp(rows);
+            int rcp = make_plan(tmp, pde, n, h->n_sm, seg.rows, seg.nseg, a, probe);
+            if (rcp) return rcp;
+            if (rows_cost(pde, n, a->Np, seg, h->n_sm, geo) < probe.cost)
+                return run_sweep_rows(h, pde, n, seg, jobs, has_fhat, NR, NI, NB, rows, a, info, geo, h->n_sm, st);
+        }
     }
     Plan plan;
     int rc = make_plan(rows, pde, n, h->n_sm, seg.rows, seg.nseg, a, plan);

@@ -1,5 +1,6 @@
 // sweep_inst.cu -- one translation unit per (PDE, n): compiled with -DGP_PDE=<0|1|2> -DGP_N=<n>.
 #include "sweep_kernel.cuh"
+#include "sweep_rows.cuh"
 
 #define GP_CAT2(a, b, c) a##b##_##c
 #define GP_CAT(a, b, c) GP_CAT2(a, b, c)
@@ -8,5 +9,9 @@ namespace gp {
 cudaError_t GP_CAT(sweep_launch_, GP_PDE, GP_N)(const SweepParams &p, int M, int priv, int ctas, size_t smem, cudaStream_t st)
 {
     return launch_n<GP_PDE, GP_N>(p, M, priv, ctas, smem, st);
+}
+cudaError_t GP_CAT(sweep_rows_launch_, GP_PDE, GP_N)(const RowsParams &p, int grid, size_t smem, cudaStream_t st)
+{
+    return rows_launch<GP_PDE, GP_N>(p, grid, smem, st);
 }
 }  // namespace gp

@@ -1,0 +1,375 @@
+// sweep_rows.cuh -- row-partitioned variant of the coefficient sweep ("grid teams"), for grids with FEW parameters.
+//
+// Same arithmetic as sweep_kernel.cuh (reference: KG_optimizer.py:34-68 + KG_models.py:28-50 per epoch, Burgers / Allen-Cahn
+// likewise), different decomposition.  The main kernel gives every warp (or team of <= 8 warps of ONE CTA) a set of
+// parameters and streams ALL rows past it every epoch; with ~100..1000 parameters that leaves SMs idle (100 work items on
+// 148 SMs), makes every CTA pull the whole stream through L2 once per epoch (2.8 MB x 128 CTAs x 2000 epochs for the
+// default Burgers grid) and, at 10^6 rows, turns the sweep into an L2 -> SM streaming problem.  Here
+//   * the ROWS are split across all CTAs of a cooperative grid (a balanced, contiguous share of every segment per CTA); if a
+//     CTA's share fits in shared memory it is loaded ONCE and stays resident for all epochs, otherwise the residual rows are
+//     streamed chunk by chunk, each row exactly once per epoch chip-wide;
+//   * EVERY parameter is processed by EVERY CTA: thread = (parameter set of M parameters, row slice); c[M][N], grad[M][N] in
+//     registers; rows are read from shared memory as LDS.128, broadcast across the parameter sets of a warp;
+//   * the linear operator is never materialised ("T-free"): t = P_a.c + tp0 (P_b.c) + tp1 (P.c) and
+//     grad += first P_a + (tp0 first) P_b + (...) P -- 6n (KG, AC) / 8n (Burgers) FMAs per row and parameter instead of
+//     4n / 6n, in exchange for which any M parameters can share a thread (no sibling structure needed: Burgers and
+//     Allen-Cahn grids have none);
+//   * per epoch the partial gradients / losses go through global memory: CTA partials -> grid barrier -> every
+//     (parameter, component) pair is summed over the CTAs in fixed order by ONE thread of the grid, which also applies
+//     c <- c - lr g and keeps the loss bookkeeping (final, min-prefix, trace) -> grid barrier -> threads reload their c.
+// Results differ from the main kernel only by summation order and the fused T (within the 1e-5 parity tolerance).
+#pragma once
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace gp {
+
+namespace cgx = cooperative_groups;
+
+constexpr int ROWS_THREADS = 256;
+constexpr int ROWS_M = 4;                      // parameters per thread
+constexpr int ROWS_MAX_PARAMS = ROWS_THREADS * ROWS_M;
+
+struct RowsParams {
+    const float *packed;                       // tile stream of the main kernel (RT_PRIV-row tiles, SlotFloats per tile)
+    int   nseg;
+    int   seg_rows[MAX_SEG];                   // rows per segment
+    int   seg_tile0[MAX_SEG];                  // first tile of each segment in the stream
+    int   slot;                                // floats per tile slot
+    int   chunk_rows;                          // residual rows that fit in the streaming buffer (multiple of 4)
+    float invR, invI, invB, fac1, fac2, fac3, lr;
+    int   epochs, rec_every, nrec, has_fhat;
+    int   Np, npsp, rs;                        // parameters, padded parameter sets (power of two), row slices = 256 / npsp
+    const float4 *pp;                          // [Np] (tp0, tp1, sp0, sp1)
+    const float *c0; int c0_per_param;
+    float *c_out, *f_out, *m_out, *trace;
+    float *cglob;                              // [Np][N]   current coefficients
+    float *partial;                            // [grid][Np][N+1]
+};
+
+// rows [lo, hi) of `total` owned by CTA b of G (balanced to one row)
+__device__ __forceinline__ void rows_share(int total, int b, int G, int &lo, int &hi)
+{
+    lo = (int)(((long long)total * b) / G);
+    hi = (int)(((long long)total * (b + 1)) / G);
+}
+
+// copy rows [r0, r0 + nr) of one segment from the tile stream into a shared-memory region laid out
+// [block][quad][row][4] then [vec][row]; NQX quads per block are kept
+template <int NARR, int NVEC, int NQX>
+__device__ __forceinline__ void rows_load(const RowsParams &p, int seg, int r0, int nr, int cap, float *dst)
+{
+    constexpr int RT = RT_PRIV;
+    const int per_row = NARR * NQX;
+    for (int e = threadIdx.x; e < nr * per_row; e += ROWS_THREADS) {
+        const int r = e % nr, bq = e / nr, blk = bq / NQX, q = bq % NQX;
+        const int row = r0 + r;
+        const float *src = p.packed + (size_t)(p.seg_tile0[seg] + row / RT) * p.slot + blk * 16 * RT + q * 4 * RT + (row % RT) * 4;
+        *reinterpret_cast<float4 *>(dst + ((blk * NQX + q) * cap + r) * 4) = *reinterpret_cast<const float4 *>(src);
+    }
+    for (int e = threadIdx.x; e < nr * NVEC; e += ROWS_THREADS) {
+        const int r = e % nr, v = e / nr, row = r0 + r;
+        dst[NARR * NQX * cap * 4 + v * cap + r] = p.packed[(size_t)(p.seg_tile0[seg] + row / RT) * p.slot + NARR * 16 * RT + v * RT + (row % RT)];
+    }
+}
+
+template <int NQX>
+__device__ __forceinline__ void rows_ld(const float *blk, int cap, int r, float (&v)[4 * NQX])
+{
+#pragma unroll
+    for (int q = 0; q < NQX; ++q) {
+        const float4 x = *reinterpret_cast<const float4 *>(blk + (q * cap + r) * 4);
+        v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+    }
+}
+
+template <int PDE, int N>
+__global__ void __launch_bounds__(ROWS_THREADS, 1) sweep_rows_kernel(const RowsParams p)
+{
+    using TR = PdeTraits<PDE>;
+    constexpr int M = ROWS_M;
+    constexpr int NQX = (N + 3) / 4;
+    constexpr int NV = N + 1;
+    constexpr int NARR = TR::NARR, NVEC = TR::NVEC;
+    cgx::grid_group grid = cgx::this_grid();
+    extern __shared__ __align__(16) float rsm[];
+    const int b = blockIdx.x, G = gridDim.x, tid = threadIdx.x;
+    const int ps = tid & (p.npsp - 1), rs = tid / p.npsp, RS = p.rs;
+
+    // ---- this CTA's share of every segment; shared-memory regions
+    int lo[MAX_SEG], hi[MAX_SEG], cap[MAX_SEG];
+    float *reg[MAX_SEG];
+    int off = 0;
+    const int row_floats = NARR * NQX * 4 + NVEC;
+    for (int s = 0; s < p.nseg; ++s) {
+        rows_share(p.seg_rows[s], b, G, lo[s], hi[s]);
+        int n = hi[s] - lo[s];
+        if (s == 0 && n > p.chunk_rows) n = p.chunk_rows;               // residual rows are streamed through one chunk buffer
+        cap[s] = (n + 3) & ~3;
+        if (cap[s] < 4) cap[s] = 4;
+        reg[s] = rsm + off;
+        off += cap[s] * row_floats;
+        off = (off + 3) & ~3;
+    }
+    float *red = rsm + off;                                            // [RS][npsp * M][NV]   (RS > 1 only)
+    const int res_rows = hi[0] - lo[0];
+    const bool resident = res_rows <= cap[0];
+    for (int s = resident ? 0 : 1; s < p.nseg; ++s) rows_load<NARR, NVEC, NQX>(p, s, lo[s], hi[s] - lo[s], cap[s], reg[s]);
+    __syncthreads();
+
+    // ---- parameters of this thread
+    float c[M][N], g[M][N];
+    float tp0[M], tp1[M], sp0[M], sp1[M];
+    bool valid[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const int pi = ps * M + m;
+        valid[m] = pi < p.Np;
+        const float4 q = valid[m] ? p.pp[pi] : make_float4(0.f, 0.f, 0.f, 0.f);
+        tp0[m] = q.x; tp1[m] = q.y; sp0[m] = q.z; sp1[m] = q.w;
+#pragma unroll
+        for (int k = 0; k < N; ++k) c[m][k] = valid[m] ? (p.c0_per_param ? p.c0[(size_t)pi * N + k] : p.c0[k]) : 0.f;
+    }
+    const bool has_fhat = p.has_fhat != 0;
+    const int Q = p.Np * NV;
+    const int gthreads = G * ROWS_THREADS, gtid = b * ROWS_THREADS + tid;
+
+    for (int j = 0; j <= p.epochs; ++j) {
+        float lacc[M], lsum[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            lacc[m] = 0.f; lsum[m] = 0.f;
+#pragma unroll
+            for (int k = 0; k < N; ++k) g[m][k] = 0.f;
+        }
+        // ------------------------------ segment 0: PDE residual rows (resident, or streamed chunk by chunk)
+        for (int r0 = 0; r0 < res_rows; r0 += cap[0]) {
+            const int nr = min(cap[0], res_rows - r0);
+            if (!resident) {
+                __syncthreads();                                        // previous chunk fully consumed
+                rows_load<NARR, NVEC, NQX>(p, 0, lo[0] + r0, nr, cap[0], reg[0]);
+                __syncthreads();
+            }
+            const float *A0 = reg[0], *A1 = A0 + NQX * cap[0] * 4, *A2 = A1 + NQX * cap[0] * 4;
+            const float *A3 = A2 + NQX * cap[0] * 4;                    // Burgers only
+            const float *V0 = reg[0] + NARR * NQX * cap[0] * 4, *V1 = V0 + cap[0];
+            for (int r = rs; r < nr; r += RS) {
+                float Pa[4 * NQX], Pb[4 * NQX], Pv[4 * NQX];
+                rows_ld<NQX>(A0, cap[0], r, Pa);                         // P_tt (KG) / P_t (B, AC)
+                rows_ld<NQX>(A1, cap[0], r, Pb);                         // P_xx
+                float forcing = 0.f, fh = 0.f;
+                if constexpr (PDE == PDE_KG) { forcing = V0[r]; if (has_fhat) fh = V1[r]; }
+                else { if (has_fhat) fh = V0[r]; }
+                if constexpr (PDE == PDE_B) {
+                    float Px[4 * NQX];
+                    rows_ld<NQX>(A2, cap[0], r, Px);
+                    rows_ld<NQX>(A3, cap[0], r, Pv);
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        float u = 0.f, ux = 0.f, a = 0.f, bb = 0.f;
+#pragma unroll
+                        for (int k = 0; k < N; ++k) {
+                            u = fmaf(Pv[k], c[m][k], u); ux = fmaf(Px[k], c[m][k], ux);
+                            a = fmaf(Pa[k], c[m][k], a); bb = fmaf(Pb[k], c[m][k], bb);
+                        }
+                        const float first = fmaf(u, ux, fmaf(tp0[m], bb, a));        // (P_t - nu P_xx).c + u u_x   B_optimizer.py:36-40
+                        const float dl = first - fh;
+                        lacc[m] = fmaf(dl, dl, lacc[m]);
+                        const float wb = tp0[m] * first, wx = first * u, wp = first * ux;
+#pragma unroll
+                        for (int k = 0; k < N; ++k)
+                            g[m][k] = fmaf(wp, Pv[k], fmaf(wx, Px[k], fmaf(wb, Pb[k], fmaf(first, Pa[k], g[m][k]))));
+                    }
+                } else {
+                    rows_ld<NQX>(A2, cap[0], r, Pv);                     // P
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        float u = 0.f, a = 0.f, bb = 0.f;
+#pragma unroll
+                        for (int k = 0; k < N; ++k) {
+                            u = fmaf(Pv[k], c[m][k], u); a = fmaf(Pa[k], c[m][k], a); bb = fmaf(Pb[k], c[m][k], bb);
+                        }
+                        const float t = fmaf(tp1[m], u, fmaf(tp0[m], bb, a));         // T.c with T = P_a + tp0 P_b + tp1 P
+                        float first, nl;
+                        if constexpr (PDE == PDE_KG) { first = fmaf(sp0[m], u * u, t) + forcing; nl = sp1[m] * u; }          // g u^2 ; 2g u
+                        else { const float u2 = u * u; first = fmaf(sp0[m], u2 * u, t); nl = sp1[m] * u2; }                  // e u^3 ; 3e u^2
+                        const float dl = first - fh;
+                        lacc[m] = fmaf(dl, dl, lacc[m]);
+                        const float wb = tp0[m] * first, wp = fmaf(first, nl, tp1[m] * first);
+#pragma unroll
+                        for (int k = 0; k < N; ++k)
+                            g[m][k] = fmaf(wp, Pv[k], fmaf(wb, Pb[k], fmaf(first, Pa[k], g[m][k])));
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            lsum[m] = lacc[m] * p.invR; lacc[m] = 0.f;
+#pragma unroll
+            for (int k = 0; k < N; ++k) g[m][k] *= p.fac1;
+        }
+        // ------------------------------ segment 1: initial-condition rows
+        {
+            const int nr = hi[1] - lo[1];
+            const float *A0 = reg[1], *A1 = A0 + NQX * cap[1] * 4;
+            const float *V0 = reg[1] + NARR * NQX * cap[1] * 4, *V1 = V0 + cap[1];
+            for (int r = rs; r < nr; r += RS) {
+                float Av[4 * NQX];
+                rows_ld<NQX>(A0, cap[1], r, Av);
+                const float tg = V0[r];
+                if constexpr (PDE == PDE_KG) {
+                    float Bv[4 * NQX];
+                    rows_ld<NQX>(A1, cap[1], r, Bv);
+                    const float tg2 = V1[r];
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        float d1 = 0.f, d2 = 0.f;
+#pragma unroll
+                        for (int k = 0; k < N; ++k) { d1 = fmaf(Av[k], c[m][k], d1); d2 = fmaf(Bv[k], c[m][k], d2); }
+                        d1 -= tg;
+                        const float e2 = d2 - tg2;
+                        lacc[m] = fmaf(d1, d1, lacc[m]); lacc[m] = fmaf(e2, e2, lacc[m]);
+                        const float w1 = p.fac3 * d1, w2 = p.fac3 * d2;               // IC_u2 absent from the update (N3)
+#pragma unroll
+                        for (int k = 0; k < N; ++k) g[m][k] = fmaf(w2, Bv[k], fmaf(w1, Av[k], g[m][k]));
+                    }
+                } else {
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        float d1 = 0.f;
+#pragma unroll
+                        for (int k = 0; k < N; ++k) d1 = fmaf(Av[k], c[m][k], d1);
+                        d1 -= tg;
+                        lacc[m] = fmaf(d1, d1, lacc[m]);
+                        const float w1 = p.fac3 * d1;
+#pragma unroll
+                        for (int k = 0; k < N; ++k) g[m][k] = fmaf(w1, Av[k], g[m][k]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < M; ++m) { lsum[m] = fmaf(lacc[m], p.invI, lsum[m]); lacc[m] = 0.f; }
+        // ------------------------------ segment 2 (3): boundary rows
+        for (int s = 2; s < TR::NSEG; ++s) {
+            const int nr = hi[s] - lo[s];
+            const float *A0 = reg[s], *A1 = A0 + NQX * cap[s] * 4, *A2 = A1 + NQX * cap[s] * 4;
+            const float *V0 = reg[s] + NARR * NQX * cap[s] * 4;
+            for (int r = rs; r < nr; r += RS) {
+                float Av[4 * NQX];
+                rows_ld<NQX>(A0, cap[s], r, Av);
+                if constexpr (PDE == PDE_AC) {                       // periodic: (P_ub c - P_lb c) * P_diff
+                    float Bv[4 * NQX], Dv[4 * NQX];
+                    rows_ld<NQX>(A1, cap[s], r, Bv);
+                    rows_ld<NQX>(A2, cap[s], r, Dv);
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        float da = 0.f, db = 0.f;
+#pragma unroll
+                        for (int k = 0; k < N; ++k) { da = fmaf(Av[k], c[m][k], da); db = fmaf(Bv[k], c[m][k], db); }
+                        const float d = da - db;
+                        lacc[m] = fmaf(d, d, lacc[m]);
+                        const float w = p.fac2 * d;
+#pragma unroll
+                        for (int k = 0; k < N; ++k) g[m][k] = fmaf(w, Dv[k], g[m][k]);
+                    }
+                } else {
+                    const float tg = V0[r];
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        float dv = 0.f;
+#pragma unroll
+                        for (int k = 0; k < N; ++k) dv = fmaf(Av[k], c[m][k], dv);
+                        const float e = dv - tg;
+                        lacc[m] = fmaf(e, e, lacc[m]);
+                        const float w = (PDE == PDE_KG) ? p.fac2 * e : p.fac2 * dv;   // Burgers: BC_u absent from the update (N3)
+#pragma unroll
+                        for (int k = 0; k < N; ++k) g[m][k] = fmaf(w, Av[k], g[m][k]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < M; ++m) lsum[m] = fmaf(lacc[m], p.invB, lsum[m]);
+
+        // ------------------------------ CTA partial: sum over the row slices (fixed order), write [Np][NV] to global
+        float *mine = p.partial + (size_t)b * Q;
+        if (RS == 1) {
+#pragma unroll
+            for (int m = 0; m < M; ++m)
+                if (valid[m]) {
+                    float *dst = mine + (size_t)(ps * M + m) * NV;
+#pragma unroll
+                    for (int k = 0; k < N; ++k) dst[k] = g[m][k];
+                    dst[N] = lsum[m];
+                }
+        } else {
+            const int plane = p.npsp * M * NV;
+            float *my = red + (size_t)rs * plane + (size_t)ps * M * NV;
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+#pragma unroll
+                for (int k = 0; k < N; ++k) my[m * NV + k] = g[m][k];
+                my[m * NV + N] = lsum[m];
+            }
+            __syncthreads();
+            for (int e = tid; e < Q; e += ROWS_THREADS) {
+                float s = 0.f;
+                for (int q = 0; q < RS; ++q) s += red[(size_t)q * plane + e];
+                mine[e] = s;
+            }
+        }
+        __threadfence();
+        grid.sync();
+
+        // ------------------------------ owners: one thread of the grid per (parameter, component)
+        const bool last = (j == p.epochs);
+        const bool rec = p.trace != nullptr && p.rec_every > 0 && (j % p.rec_every) == 0;
+        for (int e = gtid; e < Q; e += gthreads) {
+            float s = 0.f;
+            for (int q = 0; q < G; ++q) s += __ldcg(p.partial + (size_t)q * Q + e);        // written by other CTAs: bypass L1
+            const int pi = e / NV, v = e % NV;
+            if (v < N) {
+                const float cur = (j == 0) ? (p.c0_per_param ? p.c0[(size_t)pi * N + v] : p.c0[v]) : __ldcg(p.cglob + (size_t)pi * N + v);
+                if (last) { if (p.c_out) p.c_out[(size_t)pi * N + v] = cur; }
+                else p.cglob[(size_t)pi * N + v] = __fsub_rn(cur, __fmul_rn(p.lr, s));
+            } else {
+                if (rec) p.trace[(size_t)pi * p.nrec + j / p.rec_every] = s;
+                if (last) { p.f_out[pi] = s; if (p.epochs == 0) p.m_out[pi] = __int_as_float(0x7f800000); }
+                else {
+                    const float mprev = (j == 0) ? __int_as_float(0x7f800000) : __ldcg(p.m_out + pi);
+                    p.m_out[pi] = (s < mprev) ? s : mprev;
+                }
+            }
+        }
+        if (last) break;
+        __threadfence();
+        grid.sync();
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+            if (valid[m]) {
+                const float *src = p.cglob + (size_t)(ps * M + m) * N;
+#pragma unroll
+                for (int k = 0; k < N; ++k) c[m][k] = __ldcg(src + k);
+            }
+    }
+}
+
+struct RowsLaunch { int grid; size_t smem; };
+
+template <int PDE, int N>
+cudaError_t rows_launch(const RowsParams &p, int grid, size_t smem, cudaStream_t st)
+{
+    auto kern = sweep_rows_kernel<PDE, N>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    RowsParams pp = p;
+    void *args[] = {&pp};
+    return cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(ROWS_THREADS), args, smem, st);
+}
+
+typedef cudaError_t (*rows_launch_fn)(const RowsParams &p, int grid, size_t smem, cudaStream_t st);
+
+}  // namespace gp

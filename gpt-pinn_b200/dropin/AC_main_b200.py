@@ -116,6 +116,7 @@ def main(argv=None):
     out_BC_ub_x, out_BC_lb_x, out_BC_diff_x = z(BC_size), z(BC_size), z(BC_size)
     out_test = z(test_size)
     generation_time, sa_time, sa_final = np.zeros(n_neurons), np.zeros(n_neurons), np.zeros((n_neurons, 4))
+    exact_err = float("nan")
 
     # ---- greedy loop (AC_main.py:340-410)
     t_total = time.time()
@@ -130,6 +131,12 @@ def main(argv=None):
         sa_time[i] = (time.time() - t1) / 60
         sa_final[i] = sa.loss_and_grad().tolist()
         print(f"PINN time: {sa_time[i]} minutes\n")
+        if abs(lam_i - 1e-4) < 1e-12 and abs(eps_i - 5.0) < 1e-12:
+            # AC.mat holds the spectral solution for (lambda, eps) = (1e-4, 5): the one neuron whose full-order solution is known
+            Xg, Tg = np.meshgrid(x.flatten(), t.flatten(), indexing="ij")
+            pred = sa.predict(T(np.stack((Xg.flatten(), Tg.flatten()), 1))).cpu().numpy().reshape(exact_u.shape)
+            exact_err = float(np.linalg.norm(pred - exact_u) / np.linalg.norm(exact_u))
+            print(f"SA-PINN relative L2 error against the exact solution of AC.mat (lambda=1e-4, eps=5): {exact_err}\n")
         SA_w, SA_b = sa.weights_for_P()
         PINN = P(SA_w, SA_b, layers_sa).to(device)
 
@@ -172,6 +179,7 @@ def main(argv=None):
     sv("total_time.dat", np.array([total_time])); sv("xt_resid.dat", xt_resid.detach().cpu().numpy()); sv("ac_test.dat", ac_test)
     sv("xt_test.dat", xt_test.cpu().numpy()); sv("test_gpt_losses.dat", test_gpt_losses); sv("test_gpt_soln.dat", test_gpt_soln)
     sv("test_gpt_time.dat", test_gpt_time + total_time)
+    sv("sa_pinn_rel_l2_vs_exact.dat", np.array([exact_err]))
     sv("sa_pinn_time.dat", sa_time); sv("sa_pinn_final_losses.dat", sa_final)      # extra: per-neuron SA-PINN minutes, (total, mse_u, mse_b, mse_f)
     params = {"device": device, "domain": {"xi": -1, "xf": 1, "ti": 0, "tf": 1},
               "data sizes": {"N_f": N_f, "N_test": xt_size, "BC_pts": BC_size, "N0": IC_size}, "layers_pinn": layers_sa,
@@ -180,7 +188,7 @@ def main(argv=None):
               "test cases": test_cases, "epochs gpt test": args.epochs_gpt_test, "seed": args.seed}
     np.save(os.path.join(args.out, "params.npy"), params)
     print(f"End: {datetime.now()}\n")
-    return dict(neurons=neurons, loss_list=loss_list, total_time=total_time, sa_time=sa_time, sa_final=sa_final)
+    return dict(neurons=neurons, loss_list=loss_list, total_time=total_time, sa_time=sa_time, sa_final=sa_final, exact_err=exact_err)
 
 
 if __name__ == "__main__":
