@@ -422,7 +422,7 @@ struct Segments { long long rows[MAX_SEG]; int nseg; };
 // ------------------------------------------------------------------------------------------
 struct RowsGeom { int npsp, rs, chunk_rows; size_t smem; bool ok; };
 
-static RowsGeom rows_geometry(int pde, int n, int Np, const Segments &seg, int G)
+static RowsGeom rows_geometry(int pde, int n, int Np, const Segments &seg, int G, int chunk_override = 0)
 {
     RowsGeom g = {1, ROWS_THREADS, 0, 0, false};
     if (Np < 1 || Np > ROWS_MAX_PARAMS) return g;
@@ -446,6 +446,7 @@ static RowsGeom rows_geometry(int pde, int n, int Np, const Segments &seg, int G
     long long cap0 = (long long)((budget - fl) / row_floats) & ~3LL;
     cap0 = std::min<long long>(cap0, 2048);                              // streaming chunk: no need for more
     g.chunk_rows = (int)std::min<long long>(share0, cap0);
+    if (chunk_override > 0) g.chunk_rows = (int)std::min<long long>(g.chunk_rows, std::max(4, (chunk_override + 3) & ~3));   // tests: force streaming
     g.smem = (fl + (size_t)g.chunk_rows * row_floats + 8) * sizeof(float);
     g.ok = true;
     return g;
@@ -549,7 +550,7 @@ static int run_sweep(gptpinn_handle *h, int pde, int n, const Segments &seg, Pac
     if (a->cfg_mode == 3 || (a->cfg_mode == 0 && !a->bound_dev && a->Np <= ROWS_MAX_PARAMS)) {
         int coop = 0;
         CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-        const RowsGeom geo = rows_geometry(pde, n, a->Np, seg, h->n_sm);
+        const RowsGeom geo = rows_geometry(pde, n, a->Np, seg, h->n_sm, a->cfg_mode == 3 ? a->cfg_W : 0);
         if (a->cfg_mode == 3) {
             if (a->bound_dev) return fail(GPTPINN_E_INVALID, "bound_dev (early exit) is not available in the row-partitioned kernel");
             if (!coop || !geo.ok) return fail(GPTPINN_E_UNSUPPORTED, "row-partitioned kernel: needs <= %d parameters, cooperative launch and the boundary rows in shared memory", ROWS_MAX_PARAMS);

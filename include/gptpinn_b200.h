@@ -118,7 +118,10 @@ typedef struct {
     /* tuning override, 0 = let the library choose: parameters per thread (M), sibling lanes
      * per warp (SL, power of two <= 32), warps per CTA (W).                                   */
     int           cfg_M, cfg_SL, cfg_W;
-    int           cfg_mode;    /* 0 = auto, 1 = shared-ring kernel, 2 = private-ring kernel      */
+    int           cfg_mode;    /* 0 = auto, 1 = shared-ring kernel, 2 = private-ring kernel, 3 = row-partitioned kernel
+                                * (few parameters: rows split over all CTAs of a cooperative grid, every CTA processes
+                                * every parameter, per-epoch reduction through global memory; needs Np <= 1024, no
+                                * bound_dev; with cfg_mode 3, cfg_W > 0 caps the residual rows per streaming chunk)      */
     int           cfg_K;       /* 0 = auto; private-ring kernel: warps that team up on one work item
                                 * (1, 2, 4 or 8): they split the tiles of a pass and sum their gradients   */
     /* Optional early exit with the reference's semantics (KG_train.py:31-33 `if loss < largest_loss: break`):
