@@ -490,9 +490,9 @@ def main():
 
     infos, paths = [], []
 
-    def run15(rows, _c0, epochs=args.epochs, bound=None):
+    def run15(rows, _c0, epochs=args.epochs, **kw):
         r = sweep.kg_sweep(rows, c0, d["out"], d["out_xx"], d["out_tt"], d["out_IC"], d["out_IC_t"], d["out_BC"],
-                           d["xcos"], d["f_hat"], d["IC_u1"], d["IC_u2"], d["BC_u"], epochs, LR, want_c=False, cfg=cfg, bound=bound)
+                           d["xcos"], d["f_hat"], d["IC_u1"], d["IC_u2"], d["BC_u"], epochs, LR, want_c=False, cfg=cfg, **kw)
         infos.append(r["info"])
         return r
 

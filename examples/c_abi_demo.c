@@ -9,6 +9,7 @@
  */
 #include <math.h>
 #include <stdio.h>
+#include <string.h>
 #include <stdlib.h>
 
 #include <cuda_runtime.h>
@@ -75,6 +76,7 @@ int main(void)
     CK(cudaMalloc((void **)&idx, sizeof(int)));
 
     gptpinn_sweep_args a;
+    memset(&a, 0, sizeof(a));            /* optional fields (tuning overrides, early-exit bound, fused arg-max key): off */
     a.grid_host = grid; a.Np = Np; a.c0_dev = c0; a.c0_per_param = 0; a.epochs = epochs; a.lr = 0.025; a.rec_every = 0;
     a.c_out_dev = NULL; a.f_out_dev = f; a.m_out_dev = m; a.trace_dev = NULL;
     a.cfg_M = a.cfg_SL = a.cfg_W = a.cfg_mode = a.cfg_K = 0;

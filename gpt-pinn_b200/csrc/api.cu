@@ -518,6 +518,7 @@ static int run_sweep_rows(gptpinn_handle *h, int pde, int n, const Segments &seg
     p.c0 = a->c0_dev; p.c0_per_param = a->c0_per_param;
     p.c_out = a->c_out_dev; p.f_out = a->f_out_dev; p.m_out = a->m_out_dev;
     p.trace = p.rec_every > 0 ? a->trace_dev : nullptr;
+    p.key_out = a->key_out_dev; p.key_index = a->key_index_dev;
     p.cglob = (float *)((char *)h->rows_ws + pp_b);
     p.partial = (float *)((char *)h->rows_ws + pp_b + cg_b);
     rows_launch_fn fn = kRowsLaunch[pde][n - 1];
@@ -627,6 +628,7 @@ static int run_sweep(gptpinn_handle *h, int pde, int n, const Segments &seg, Pac
     p.counter = h->counter;
     p.K = plan.priv ? plan.K : 1;
     p.bound = plan.priv ? a->bound_dev : nullptr;
+    p.key_out = a->key_out_dev; p.key_index = a->key_index_dev;
 
     const size_t tblk = (size_t)(n / 4 + 1) * 4 * RT * 4;                       // shared ring only: per-warp T block
     const size_t smem = plan.priv

@@ -81,6 +81,8 @@ struct SweepParams {
     int            rounds;           // shared-ring kernels: static rounds of gridDim.x * W items
     unsigned int  *counter;          // private-ring kernels: global work-item ticket (zeroed before launch)
     const float   *bound;            // private-ring kernels: [Np] per-parameter early-exit bound B_p <= L_seq(p), or nullptr
+    unsigned long long *key_out;     // optional: atomicMax of (float_bits(final loss) << 32) | (0xFFFFFFFF - global index) over all rows
+    const int     *key_index;        // optional [Np]: global grid index of each row (nullptr: the row number)
     int            K;                // private-ring kernels: warps per team (power of two dividing W); a team shares one
                                      // work item, its warps take every K-th tile and sum their gradients once per epoch
 };

@@ -582,6 +582,11 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                     if (last || leave) {
                         p.f_out[oi] = loss;
                         p.m_out[oi] = leave ? loss : mn[m];
+                        // fused arg-max epilogue: one 64-bit key per GPU = first arg-max of the final losses
+                        // (losses >= 0: bit order = numeric order; complemented index: the first row wins ties; NaN never enters)
+                        if (last && p.key_out != nullptr && loss > 0.f)
+                            atomicMax(p.key_out, ((unsigned long long)__float_as_uint(loss) << 32) |
+                                                     (unsigned long long)(0xFFFFFFFFu - (unsigned)(p.key_index ? p.key_index[oi] : oi)));
                         if (p.c_out != nullptr) {
 #pragma unroll
                             for (int k = 0; k < N; ++k) p.c_out[(size_t)oi * N + k] = c[m][k];

@@ -44,6 +44,7 @@ struct RowsParams {
     const float4 *pp;                          // [Np] (tp0, tp1, sp0, sp1)
     const float *c0; int c0_per_param;
     float *c_out, *f_out, *m_out, *trace;
+    unsigned long long *key_out; const int *key_index;      // fused arg-max key (see SweepParams)
     float *cglob;                              // [Np][N]   current coefficients
     float *partial;                            // [grid][Np][N+1]
 };
@@ -337,7 +338,13 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) sweep_rows_kernel(const RowsP
                 else p.cglob[(size_t)pi * N + v] = __fsub_rn(cur, __fmul_rn(p.lr, s));
             } else {
                 if (rec) p.trace[(size_t)pi * p.nrec + j / p.rec_every] = s;
-                if (last) { p.f_out[pi] = s; if (p.epochs == 0) p.m_out[pi] = __int_as_float(0x7f800000); }
+                if (last) {
+                    p.f_out[pi] = s;
+                    if (p.epochs == 0) p.m_out[pi] = __int_as_float(0x7f800000);
+                    if (p.key_out != nullptr && s > 0.f)
+                        atomicMax(p.key_out, ((unsigned long long)__float_as_uint(s) << 32) |
+                                                 (unsigned long long)(0xFFFFFFFFu - (unsigned)(p.key_index ? p.key_index[pi] : pi)));
+                }
                 else {
                     const float mprev = (j == 0) ? __int_as_float(0x7f800000) : __ldcg(p.m_out + pi);
                     p.m_out[pi] = (s < mprev) ? s : mprev;

@@ -11,10 +11,10 @@ def offline_generation(ac_train, c_initial, xt_size, IC_size, BC_size, IC_u,
                        f_hat, epochs_gpt, lr_gpt):
     grid = np.asarray(ac_train, dtype=np.float64).reshape(-1, 2)
 
-    def run(rows, _c0, epochs=epochs_gpt, bound=None):
+    def run(rows, _c0, epochs=epochs_gpt, **kw):
         return sweep.ac_sweep(rows, c_initial, out, out_t, out_xx, out_IC, out_BC_ub, out_BC_lb, out_BC_diff,
                               out_BC_ub_x, out_BC_lb_x, out_BC_diff_x, f_hat, IC_u, epochs, lr_gpt,
-                              want_c=True, bound=bound)
+                              want_c=True, **kw)
 
     largest_loss, idx, res = offline.greedy_select(run, grid, epochs_gpt, want_c=True)
     if idx < 0:

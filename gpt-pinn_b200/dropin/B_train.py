@@ -44,9 +44,9 @@ def offline_generation(nu_train, xt_size, IC_size, BC_size, IC_u, BC_u, out,
     grid = np.asarray(nu_train, dtype=np.float64).reshape(-1)
     c0 = torch.from_numpy(initial_coefficients(grid, neuron_params, neuron_cnt)).to(out.device)
 
-    def run(rows, c0_rows, epochs=epochs_gpt, bound=None):
+    def run(rows, c0_rows, epochs=epochs_gpt, **kw):
         return sweep.b_sweep(rows, c0_rows, out, out_x, out_t, out_xx, out_IC, out_BC, f_hat, IC_u, BC_u,
-                             epochs, lr_gpt, want_c=False, bound=bound)
+                             epochs, lr_gpt, want_c=False, **kw)
 
     largest_loss, idx, _ = offline.greedy_select(run, grid, epochs_gpt, c0=c0)
     if idx < 0:

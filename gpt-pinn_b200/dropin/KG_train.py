@@ -18,9 +18,9 @@ def offline_generation(kg_train, c_initial, xt_size, IC_size, BC_size, IC_u1,
                        out_IC_t, out_BC, f_hat, epochs_gpt, lr_gpt):
     grid = np.asarray(kg_train, dtype=np.float64).reshape(-1, 3)
 
-    def run(rows, _c0, epochs=epochs_gpt, bound=None):
+    def run(rows, _c0, epochs=epochs_gpt, **kw):
         return sweep.kg_sweep(rows, c_initial, out, out_xx, out_tt, out_IC, out_IC_t, out_BC,
-                              xcos_x2cos2, f_hat, IC_u1, IC_u2, BC_u, epochs, lr_gpt, want_c=False, bound=bound)
+                              xcos_x2cos2, f_hat, IC_u1, IC_u2, BC_u, epochs, lr_gpt, want_c=False, **kw)
 
     largest_loss, idx, _ = offline.greedy_select(run, grid, epochs_gpt, group_cols=(0, 1))
     if idx < 0:

@@ -43,7 +43,7 @@ class SweepArgs(C.Structure):
                 ("c_out_dev", C.c_void_p), ("f_out_dev", C.c_void_p), ("m_out_dev", C.c_void_p),
                 ("trace_dev", C.c_void_p),
                 ("cfg_M", C.c_int), ("cfg_SL", C.c_int), ("cfg_W", C.c_int), ("cfg_mode", C.c_int),
-                ("cfg_K", C.c_int), ("bound_dev", C.c_void_p)]
+                ("cfg_K", C.c_int), ("bound_dev", C.c_void_p), ("key_out_dev", C.c_void_p), ("key_index_dev", C.c_void_p)]
 
 
 class SweepInfo(C.Structure):

@@ -113,6 +113,8 @@ def sharded_sweep(run, grid, c0=None, want_c=False, gather_c=False, group_cols=N
     c0_loc = c0
     if c0 is not None and c0.dim() == 2:
         c0_loc = c0[lo:hi] if order is None else c0[torch.from_numpy(rows).to(c0.device)]
+    if not gather and _dist() is not None:
+        kw["key_index"] = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.int32))      # fused arg-max epilogue in the kernel
     if bound is not None:
         kw["bound"] = (bound[lo:hi] if order is None else bound[torch.from_numpy(rows).to(bound.device)]).contiguous()
     res = run(grid[rows], c0_loc, **kw)
@@ -165,7 +167,9 @@ def select_sharded(res):
     dev = f.device
     n_rows = res["n_rows"]
     gidx = torch.from_numpy(np.asarray(res["rows"], dtype=np.int64)).to(dev)
-    if f.numel():
+    if res.get("local") is not None and res["local"].get("key") is not None:
+        key = res["local"]["key"].clone()                            # reduced by the sweep kernel's epilogue (atomicMax)
+    elif f.numel():
         key = pack_keys(f, gidx).max().reshape(1)
     else:
         key = torch.zeros(1, dtype=torch.int64, device=dev)

@@ -3,8 +3,7 @@
 `train_fused` runs every epoch inside one persistent cooperative CUDA kernel (gptpinn_pinn_train):
 forward-mode derivative channels, PDE residual, hand-derived reverse pass, gradient reduction and
 torch.optim.Adam's update, with the weights resident on the device for the whole run.
-`train_adam` is the host loop over torch autograd; it is kept only for callers that hand over an
-arbitrary loss closure (it is not used by the drop-in pinn_train for Klein-Gordon / Burgers).
+There is no torch-autograd training loop in this package: a network shape the kernel does not cover is an error.
 """
 import ctypes as C
 
@@ -110,24 +109,3 @@ def train_fused(model, pde, pde_params, xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC
 def epochs_done(result):
     """Epochs entered (syncs)."""
     return int(result["status"][1:2].view(torch.int32).item())
-
-
-def train_adam(model, loss_fn, epochs, lr, tol=None, record_every=None):
-    """Host loop: `epochs` Adam steps on an arbitrary loss closure (torch autograd).  With `tol`, stops
-    *before* the step once loss < tol (B_train.py:84).  Returns the final loss, or with `record_every`
-    a dict {epoch: loss evaluated after that epoch's step}."""
-    opt = torch.optim.Adam(model.parameters(), lr=lr)
-    loss = None
-    rec = {}
-    for i in range(1, epochs + 1):
-        loss = loss_fn()
-        if tol is not None and loss < tol:
-            break
-        opt.zero_grad()
-        loss.backward()
-        opt.step()
-        if record_every and (i % record_every == 0 or i == epochs):
-            rec[i] = loss_fn().item()
-    if record_every:
-        return rec
-    return float(loss.item()) if loss is not None else float("nan")

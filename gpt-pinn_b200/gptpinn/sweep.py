@@ -79,7 +79,7 @@ def _opt_vec(t, name, keep, rows):
     return _vec(t, name, keep, rows)
 
 
-def _run(fn_name, prob, keep, grid, gcols, n, c0, epochs, lr, rec_every, want_c, cfg, device, bound=None):
+def _run(fn_name, prob, keep, grid, gcols, n, c0, epochs, lr, rec_every, want_c, cfg, device, bound=None, key_index=None):
     grid = np.ascontiguousarray(np.asarray(grid, dtype=np.float64).reshape(-1, gcols))
     Np = grid.shape[0]
     c0 = _req_cuda(c0, "c_initial")
@@ -115,6 +115,14 @@ def _run(fn_name, prob, keep, grid, gcols, n, c0, epochs, lr, rec_every, want_c,
         if bound.numel() != Np:
             raise ValueError(f"bound has {bound.numel()} entries, expected {Np}")
         args.bound_dev = bound.data_ptr()
+    key = None
+    if key_index is not None:
+        # fused arg-max epilogue: the kernel maximises (float_bits(f) << 32) | ~global_index over this call's rows
+        key_index = key_index.to(device=device, dtype=torch.int32).contiguous()
+        if key_index.numel() != Np:
+            raise ValueError(f"key_index has {key_index.numel()} entries, expected {Np}")
+        key = torch.zeros(1, dtype=torch.int64, device=device)
+        args.key_out_dev, args.key_index_dev = key.data_ptr(), key_index.data_ptr()
     if cfg:
         args.cfg_M, args.cfg_SL, args.cfg_W = (int(cfg.get("M", 0)), int(cfg.get("SL", 0)), int(cfg.get("W", 0)))
         args.cfg_mode = int(cfg.get("mode", 0))
@@ -125,11 +133,11 @@ def _run(fn_name, prob, keep, grid, gcols, n, c0, epochs, lr, rec_every, want_c,
         stream = torch.cuda.current_stream(device).cuda_stream
         rc = getattr(_lib.lib(), fn_name)(h, C.byref(prob), C.byref(args), C.byref(info), C.c_void_p(stream))
     _lib.check(rc, fn_name)
-    return dict(c=c, f=f, m=m, trace=trace, info=info.asdict(), _keep=(keep, c0, grid, bound))
+    return dict(c=c, f=f, m=m, trace=trace, key=key, info=info.asdict(), _keep=(keep, c0, grid, bound, key_index))
 
 
 def kg_sweep(grid, c0, out, out_xx, out_tt, out_IC, out_IC_t, out_BC, xcos, f_hat, IC_u1, IC_u2, BC_u,
-             epochs, lr, rec_every=0, want_c=True, cfg=None, bound=None):
+             epochs, lr, rec_every=0, want_c=True, cfg=None, bound=None, key_index=None):
     """All-epochs Klein-Gordon sweep over `grid` [Np,3] (alpha, beta, gamma)."""
     keep = []
     n = out.shape[1]
@@ -144,11 +152,11 @@ def kg_sweep(grid, c0, out, out_xx, out_tt, out_IC, out_IC_t, out_BC, xcos, f_ha
     p.ICu1 = _vec(IC_u1, "IC_u1", keep, NI)
     p.ICu2 = _opt_vec(IC_u2, "IC_u2", keep, NI)
     p.BCu = _vec(BC_u, "BC_u", keep, NB)
-    return _run("gptpinn_kg_sweep", p, keep, grid, 3, n, c0, epochs, lr, rec_every, want_c, cfg, out.device, bound)
+    return _run("gptpinn_kg_sweep", p, keep, grid, 3, n, c0, epochs, lr, rec_every, want_c, cfg, out.device, bound, key_index)
 
 
 def b_sweep(grid, c0, out, out_x, out_t, out_xx, out_IC, out_BC, f_hat, IC_u, BC_u,
-            epochs, lr, rec_every=0, want_c=True, cfg=None, bound=None):
+            epochs, lr, rec_every=0, want_c=True, cfg=None, bound=None, key_index=None):
     """All-epochs Burgers sweep over `grid` [Np] (nu)."""
     keep = []
     n = out.shape[1]
@@ -161,12 +169,12 @@ def b_sweep(grid, c0, out, out_x, out_t, out_xx, out_IC, out_BC, f_hat, IC_u, BC
     p.fhat = _opt_vec(f_hat, "f_hat", keep, NR)
     p.ICu = _vec(IC_u, "IC_u", keep, NI)
     p.BCu = _opt_vec(BC_u, "BC_u", keep, NB)
-    return _run("gptpinn_b_sweep", p, keep, grid, 1, n, c0, epochs, lr, rec_every, want_c, cfg, out.device, bound)
+    return _run("gptpinn_b_sweep", p, keep, grid, 1, n, c0, epochs, lr, rec_every, want_c, cfg, out.device, bound, key_index)
 
 
 def ac_sweep(grid, c0, out, out_t, out_xx, out_IC, out_BC_ub, out_BC_lb, out_BC_diff, out_BC_ub_x,
              out_BC_lb_x, out_BC_diff_x, f_hat, IC_u, epochs, lr, rec_every=0, want_c=True, cfg=None, bound=None,
-             t_given=False):
+             t_given=False, key_index=None):
     """All-epochs Allen-Cahn sweep over `grid` [Np,2] (lambda, eps).  With t_given, `out_t` is the materialised
     T = P_t - lambda P_xx - eps P (used bit for bit; `out_xx` ignored, only eps of each row is used)."""
     keep = []
@@ -183,7 +191,7 @@ def ac_sweep(grid, c0, out, out_t, out_xx, out_IC, out_BC_ub, out_BC_lb, out_BC_
     p.fhat = _opt_vec(f_hat, "f_hat", keep, NR)
     p.ICu = _vec(IC_u, "IC_u", keep, NI)
     p.t_given = 1 if t_given else 0
-    return _run("gptpinn_ac_sweep", p, keep, grid, 2, n, c0, epochs, lr, rec_every, want_c, cfg, out.device, bound)
+    return _run("gptpinn_ac_sweep", p, keep, grid, 2, n, c0, epochs, lr, rec_every, want_c, cfg, out.device, bound, key_index)
 
 
 def argmax_scan_device(f, m):

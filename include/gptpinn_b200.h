@@ -131,6 +131,13 @@ typedef struct {
      * gptpinn_argmax_scan rejects exactly like the reference's break; rows that never fall below their bound
      * run all epochs and report exact values.  NULL = no early exit (fixed work).  Forces the private-ring kernel. */
     const float  *bound_dev;   /* [Np] or NULL                                                  */
+    /* Optional fused arg-max epilogue for sharded grids: the kernel atomically maximises, over the rows of
+     * this call, the 64-bit key (float_bits(f_out[p]) << 32) | (0xFFFFFFFF - key_index_dev[p]) into *key_out_dev (which
+     * the caller zeroes; rows with NaN or non-positive final loss do not enter).  The maximum over all ranks (one 8-byte
+     * MAX all-reduce) is the first arg-max of the final losses = the reference's selection whenever the winner's
+     * min-prefix loss is not below the largest earlier final loss (N1 guard, checked by the caller).                      */
+    unsigned long long *key_out_dev;   /* [1] or NULL                                            */
+    const int    *key_index_dev;       /* [Np] global grid index of each row, or NULL (= row number) */
 } gptpinn_sweep_args;
 
 /* filled by the sweep calls when non-NULL: what was launched (for bench.py / tests)           */

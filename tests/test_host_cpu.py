@@ -364,9 +364,14 @@ def _key_worker(rank, world, port, q):
         if case == 4:
             f[:] = 0.0                                                    # nothing exceeds 0
 
-        def run(rows, _c0, epochs=None):
+        def run(rows, _c0, epochs=None, key_index=None):
             ids = [int(np.nonzero(np.all(grid == r, axis=1))[0][0]) for r in rows]
-            return dict(f=torch.from_numpy(f[ids]), m=torch.from_numpy(m[ids]), c=None, info={})
+            assert key_index is not None and key_index.tolist() == ids      # the kernel epilogue gets the GLOBAL row indices
+            key = None
+            if case % 2 == 0:                                                # emulate the fused epilogue on half of the cases
+                ff = torch.from_numpy(f[ids])
+                key = offline.pack_keys(ff, key_index.to(torch.int64)).max().reshape(1) if len(ids) else torch.zeros(1, dtype=torch.int64)
+            return dict(f=torch.from_numpy(f[ids]), m=torch.from_numpy(m[ids]), c=None, key=key, info={})
 
         res = offline.sharded_sweep(run, grid, group_cols=(0, 1), gather=False)
         L, idx, path = offline.select_sharded(res)
