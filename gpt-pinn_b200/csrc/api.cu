@@ -443,11 +443,12 @@ static RowsGeom rows_geometry(int pde, int n, int Np, const Segments &seg, int G
     if (fl + 64 * row_floats > budget) return g;
     long long share0 = (seg.rows[0] + G - 1) / G + 1;
     share0 = std::max<long long>(4, (share0 + 3) & ~3LL);
-    long long cap0 = (long long)((budget - fl) / row_floats) & ~3LL;
-    cap0 = std::min<long long>(cap0, 2048);                              // streaming chunk: no need for more
-    g.chunk_rows = (int)std::min<long long>(share0, cap0);
-    if (chunk_override > 0) g.chunk_rows = (int)std::min<long long>(g.chunk_rows, std::max(4, (chunk_override + 3) & ~3));   // tests: force streaming
-    g.smem = (fl + (size_t)g.chunk_rows * row_floats + 8) * sizeof(float);
+    const long long cap_total = (long long)((budget - fl) / row_floats) & ~3LL;
+    int nbuf = 1;
+    if (share0 <= cap_total) g.chunk_rows = (int)share0;                // the CTA's residual share stays resident
+    else { g.chunk_rows = (int)std::min<long long>((cap_total / 2) & ~3LL, 512); nbuf = 2; }   // streamed through a double buffer
+    if (chunk_override > 0 && ((chunk_override + 3) & ~3) < g.chunk_rows) { g.chunk_rows = std::max(4, (chunk_override + 3) & ~3); nbuf = 2; }   // tests: force streaming
+    g.smem = (fl + (size_t)nbuf * g.chunk_rows * row_floats + 8) * sizeof(float);
     g.ok = true;
     return g;
 }
@@ -514,6 +515,8 @@ static int run_sweep_rows(gptpinn_handle *h, int pde, int n, const Segments &seg
     p.nrec = p.rec_every > 0 ? a->epochs / p.rec_every + 1 : 0;
     p.has_fhat = has_fhat ? 1 : 0;
     p.Np = Np; p.npsp = geo.npsp; p.rs = geo.rs;
+    p.tpp = 1;
+    while (p.tpp < 32 && (long long)Np * NV * (p.tpp * 2) <= (long long)G * ROWS_THREADS) p.tpp *= 2;
     p.pp = (const float4 *)h->rows_ws;
     p.c0 = a->c0_dev; p.c0_per_param = a->c0_per_param;
     p.c_out = a->c_out_dev; p.f_out = a->f_out_dev; p.m_out = a->m_out_dev;

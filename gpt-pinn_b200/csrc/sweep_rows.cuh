@@ -41,6 +41,7 @@ struct RowsParams {
     float invR, invI, invB, fac1, fac2, fac3, lr;
     int   epochs, rec_every, nrec, has_fhat;
     int   Np, npsp, rs;                        // parameters, padded parameter sets (power of two), row slices = 256 / npsp
+    int   tpp;                                 // lanes that share one (parameter, component) pair in the owner phase (power of two <= 32)
     const float4 *pp;                          // [Np] (tp0, tp1, sp0, sp1)
     const float *c0; int c0_per_param;
     float *c_out, *f_out, *m_out, *trace;
@@ -75,6 +76,26 @@ __device__ __forceinline__ void rows_load(const RowsParams &p, int seg, int r0, 
     }
 }
 
+// asynchronous variant (cp.async, 16-byte and 4-byte copies) for the streamed residual chunks: issue, commit, wait later
+template <int NARR, int NVEC, int NQX>
+__device__ __forceinline__ void rows_load_async(const RowsParams &p, int seg, int r0, int nr, int cap, float *dst)
+{
+    constexpr int RT = RT_PRIV;
+    const int per_row = NARR * NQX;
+    for (int e = threadIdx.x; e < nr * per_row; e += ROWS_THREADS) {
+        const int r = e % nr, bq = e / nr, blk = bq / NQX, q = bq % NQX;
+        const int row = r0 + r;
+        const float *src = p.packed + (size_t)(p.seg_tile0[seg] + row / RT) * p.slot + blk * 16 * RT + q * 4 * RT + (row % RT) * 4;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + ((blk * NQX + q) * cap + r) * 4)), "l"(src) : "memory");
+    }
+    for (int e = threadIdx.x; e < nr * NVEC; e += ROWS_THREADS) {
+        const int r = e % nr, v = e / nr, row = r0 + r;
+        const float *src = p.packed + (size_t)(p.seg_tile0[seg] + row / RT) * p.slot + NARR * 16 * RT + v * RT + (row % RT);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + NARR * NQX * cap * 4 + v * cap + r)), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 template <int NQX>
 __device__ __forceinline__ void rows_ld(const float *blk, int cap, int r, float (&v)[4 * NQX])
 {
@@ -106,11 +127,12 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) sweep_rows_kernel(const RowsP
     for (int s = 0; s < p.nseg; ++s) {
         rows_share(p.seg_rows[s], b, G, lo[s], hi[s]);
         int n = hi[s] - lo[s];
-        if (s == 0 && n > p.chunk_rows) n = p.chunk_rows;               // residual rows are streamed through one chunk buffer
+        const bool streamed = (s == 0 && n > p.chunk_rows);              // residual rows go through a double buffer of chunks
+        if (streamed) n = p.chunk_rows;
         cap[s] = (n + 3) & ~3;
         if (cap[s] < 4) cap[s] = 4;
         reg[s] = rsm + off;
-        off += cap[s] * row_floats;
+        off += cap[s] * row_floats * (streamed ? 2 : 1);
         off = (off + 3) & ~3;
     }
     float *red = rsm + off;                                            // [RS][npsp * M][NV]   (RS > 1 only)
@@ -145,16 +167,27 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) sweep_rows_kernel(const RowsP
             for (int k = 0; k < N; ++k) g[m][k] = 0.f;
         }
         // ------------------------------ segment 0: PDE residual rows (resident, or streamed chunk by chunk)
-        for (int r0 = 0; r0 < res_rows; r0 += cap[0]) {
+        const int buf_floats = cap[0] * row_floats;
+        if (!resident) rows_load_async<NARR, NVEC, NQX>(p, 0, lo[0], min(cap[0], res_rows), cap[0], reg[0]);
+        for (int r0 = 0, ci = 0; r0 < res_rows; r0 += cap[0], ++ci) {
             const int nr = min(cap[0], res_rows - r0);
+            const float *base = reg[0];
             if (!resident) {
-                __syncthreads();                                        // previous chunk fully consumed
-                rows_load<NARR, NVEC, NQX>(p, 0, lo[0] + r0, nr, cap[0], reg[0]);
+                // chunk ci is in flight in buffer ci & 1; start chunk ci + 1 into the other buffer (its previous contents were
+                // consumed before the barrier that ended the previous iteration), then wait for chunk ci only
+                const int rn = r0 + cap[0];
+                if (rn < res_rows) {
+                    rows_load_async<NARR, NVEC, NQX>(p, 0, lo[0] + rn, min(cap[0], res_rows - rn), cap[0], reg[0] + ((ci + 1) & 1) * buf_floats);
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");
+                } else {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                }
                 __syncthreads();
+                base = reg[0] + (ci & 1) * buf_floats;
             }
-            const float *A0 = reg[0], *A1 = A0 + NQX * cap[0] * 4, *A2 = A1 + NQX * cap[0] * 4;
+            const float *A0 = base, *A1 = A0 + NQX * cap[0] * 4, *A2 = A1 + NQX * cap[0] * 4;
             const float *A3 = A2 + NQX * cap[0] * 4;                    // Burgers only
-            const float *V0 = reg[0] + NARR * NQX * cap[0] * 4, *V1 = V0 + cap[0];
+            const float *V0 = base + NARR * NQX * cap[0] * 4, *V1 = V0 + cap[0];
             for (int r = rs; r < nr; r += RS) {
                 float Pa[4 * NQX], Pb[4 * NQX], Pv[4 * NQX];
                 rows_ld<NQX>(A0, cap[0], r, Pa);                         // P_tt (KG) / P_t (B, AC)
@@ -204,6 +237,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) sweep_rows_kernel(const RowsP
                     }
                 }
             }
+            if (!resident) __syncthreads();                             // this buffer is refilled two chunks ahead
         }
 #pragma unroll
         for (int m = 0; m < M; ++m) {
@@ -325,29 +359,48 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) sweep_rows_kernel(const RowsP
         __threadfence();
         grid.sync();
 
-        // ------------------------------ owners: one thread of the grid per (parameter, component)
+        // ------------------------------ owners: `tpp` lanes of the grid per (parameter, component) pair sum the G CTA
+        // partials (strided over the CTAs, four loads in flight per lane, fixed combination order => deterministic)
         const bool last = (j == p.epochs);
         const bool rec = p.trace != nullptr && p.rec_every > 0 && (j % p.rec_every) == 0;
-        for (int e = gtid; e < Q; e += gthreads) {
-            float s = 0.f;
-            for (int q = 0; q < G; ++q) s += __ldcg(p.partial + (size_t)q * Q + e);        // written by other CTAs: bypass L1
-            const int pi = e / NV, v = e % NV;
-            if (v < N) {
-                const float cur = (j == 0) ? (p.c0_per_param ? p.c0[(size_t)pi * N + v] : p.c0[v]) : __ldcg(p.cglob + (size_t)pi * N + v);
-                if (last) { if (p.c_out) p.c_out[(size_t)pi * N + v] = cur; }
-                else p.cglob[(size_t)pi * N + v] = __fsub_rn(cur, __fmul_rn(p.lr, s));
-            } else {
-                if (rec) p.trace[(size_t)pi * p.nrec + j / p.rec_every] = s;
-                if (last) {
-                    p.f_out[pi] = s;
-                    if (p.epochs == 0) p.m_out[pi] = __int_as_float(0x7f800000);
-                    if (p.key_out != nullptr && s > 0.f)
-                        atomicMax(p.key_out, ((unsigned long long)__float_as_uint(s) << 32) |
-                                                 (unsigned long long)(0xFFFFFFFFu - (unsigned)(p.key_index ? p.key_index[pi] : pi)));
+        {
+            const int tpp = p.tpp, ppw = 32 / tpp;                       // pairs per warp and step
+            const int lane = tid & 31, sub = lane & (tpp - 1);
+            const int gwarp = gtid >> 5, gwarps = gthreads >> 5;
+            for (int e0 = gwarp * ppw; e0 < Q; e0 += gwarps * ppw) {     // warp-uniform trip count (full-mask shuffles below)
+                const int e = e0 + lane / tpp;
+                const bool act = e < Q;
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                if (act) {
+                    const float *src = p.partial + e;
+                    int q = sub;
+                    for (; q + 3 * tpp < G; q += 4 * tpp) {
+                        s0 += __ldcg(src + (size_t)q * Q); s1 += __ldcg(src + (size_t)(q + tpp) * Q);
+                        s2 += __ldcg(src + (size_t)(q + 2 * tpp) * Q); s3 += __ldcg(src + (size_t)(q + 3 * tpp) * Q);
+                    }
+                    for (; q < G; q += tpp) s0 += __ldcg(src + (size_t)q * Q);
                 }
-                else {
-                    const float mprev = (j == 0) ? __int_as_float(0x7f800000) : __ldcg(p.m_out + pi);
-                    p.m_out[pi] = (s < mprev) ? s : mprev;
+                float s = (s0 + s1) + (s2 + s3);
+                for (int off = tpp >> 1; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                if (act && sub == 0) {
+                    const int pi = e / NV, v = e % NV;
+                    if (v < N) {
+                        const float cur = (j == 0) ? (p.c0_per_param ? p.c0[(size_t)pi * N + v] : p.c0[v]) : __ldcg(p.cglob + (size_t)pi * N + v);
+                        if (last) { if (p.c_out) p.c_out[(size_t)pi * N + v] = cur; }
+                        else p.cglob[(size_t)pi * N + v] = __fsub_rn(cur, __fmul_rn(p.lr, s));
+                    } else {
+                        if (rec) p.trace[(size_t)pi * p.nrec + j / p.rec_every] = s;
+                        if (last) {
+                            p.f_out[pi] = s;
+                            if (p.epochs == 0) p.m_out[pi] = __int_as_float(0x7f800000);
+                            if (p.key_out != nullptr && s > 0.f)
+                                atomicMax(p.key_out, ((unsigned long long)__float_as_uint(s) << 32) |
+                                                         (unsigned long long)(0xFFFFFFFFu - (unsigned)(p.key_index ? p.key_index[pi] : pi)));
+                        } else {
+                            const float mprev = (j == 0) ? __int_as_float(0x7f800000) : __ldcg(p.m_out + pi);
+                            p.m_out[pi] = (s < mprev) ? s : mprev;
+                        }
+                    }
                 }
             }
         }
