@@ -27,11 +27,16 @@ static const sweep_launch_fn kLaunch[3][15] = {
     {GP_ROW9(0), sweep_launch_0_10, sweep_launch_0_11, sweep_launch_0_12, sweep_launch_0_13, sweep_launch_0_14, sweep_launch_0_15},
     {GP_ROW9(1), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr},
     {GP_ROW9(2), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}};
-#define GP_RDECL(P, N) cudaError_t sweep_rows_launch_##P##_##N(const RowsParams &, int, size_t, cudaStream_t);
+#define GP_RDECL(P, N) cudaError_t sweep_rows_launch_##P##_##N(const RowsParams &, int, size_t, cudaStream_t); int sweep_rows_clusters_##P##_##N(int, size_t);
 #define GP_RDECL_ALL(P) GP_RDECL(P, 1) GP_RDECL(P, 2) GP_RDECL(P, 3) GP_RDECL(P, 4) GP_RDECL(P, 5) GP_RDECL(P, 6) GP_RDECL(P, 7) GP_RDECL(P, 8) GP_RDECL(P, 9)
 GP_RDECL_ALL(0) GP_RDECL_ALL(1) GP_RDECL_ALL(2)
 GP_RDECL(0, 10) GP_RDECL(0, 11) GP_RDECL(0, 12) GP_RDECL(0, 13) GP_RDECL(0, 14) GP_RDECL(0, 15)
 #define GP_RROW9(P) sweep_rows_launch_##P##_1, sweep_rows_launch_##P##_2, sweep_rows_launch_##P##_3, sweep_rows_launch_##P##_4, sweep_rows_launch_##P##_5, sweep_rows_launch_##P##_6, sweep_rows_launch_##P##_7, sweep_rows_launch_##P##_8, sweep_rows_launch_##P##_9
+#define GP_CROW9(P) sweep_rows_clusters_##P##_1, sweep_rows_clusters_##P##_2, sweep_rows_clusters_##P##_3, sweep_rows_clusters_##P##_4, sweep_rows_clusters_##P##_5, sweep_rows_clusters_##P##_6, sweep_rows_clusters_##P##_7, sweep_rows_clusters_##P##_8, sweep_rows_clusters_##P##_9
+static const rows_clusters_fn kRowsClusters[3][15] = {
+    {GP_CROW9(0), sweep_rows_clusters_0_10, sweep_rows_clusters_0_11, sweep_rows_clusters_0_12, sweep_rows_clusters_0_13, sweep_rows_clusters_0_14, sweep_rows_clusters_0_15},
+    {GP_CROW9(1), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr},
+    {GP_CROW9(2), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}};
 static const rows_launch_fn kRowsLaunch[3][15] = {
     {GP_RROW9(0), sweep_rows_launch_0_10, sweep_rows_launch_0_11, sweep_rows_launch_0_12, sweep_rows_launch_0_13, sweep_rows_launch_0_14, sweep_rows_launch_0_15},
     {GP_RROW9(1), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr},
@@ -283,7 +288,7 @@ static int make_plan(std::vector<ParamRow> &rows, int pde, int n, int n_sm, cons
         return fail(GPTPINN_E_INVALID, "cfg_M must be 0, 1, 2, 4 or 5");
     if (a->cfg_SL != 0 && (a->cfg_SL < 1 || a->cfg_SL > 32 || (a->cfg_SL & (a->cfg_SL - 1))))
         return fail(GPTPINN_E_INVALID, "cfg_SL must be 0 or a power of two <= 32");
-    if (a->cfg_mode < 0 || a->cfg_mode > 3) return fail(GPTPINN_E_INVALID, "cfg_mode must be 0, 1, 2 or 3");
+    if (a->cfg_mode < 0 || a->cfg_mode > 4) return fail(GPTPINN_E_INVALID, "cfg_mode must be 0 .. 4");
 
     if (a->cfg_K != 0 && !(a->cfg_K == 1 || a->cfg_K == 2 || a->cfg_K == 4 || a->cfg_K == 8))
         return fail(GPTPINN_E_INVALID, "cfg_K must be 0, 1, 2, 4 or 8");
@@ -420,16 +425,16 @@ struct Segments { long long rows[MAX_SEG]; int nseg; };
 // ------------------------------------------------------------------------------------------
 // row-partitioned kernel (sweep_rows.cuh): cost model and launch
 // ------------------------------------------------------------------------------------------
-struct RowsGeom { int npsp, rs, chunk_rows; size_t smem; bool ok; };
+struct RowsGeom { int npsp, rs, chunk_rows; size_t smem; bool ok; int S, C; };
 
-static RowsGeom rows_geometry(int pde, int n, int Np, const Segments &seg, int G, int chunk_override = 0)
+// G = CTAs that share the rows (the whole grid, or the S CTAs of a cluster); npar = parameters every such CTA works on
+// (all of them, or the cluster's share); cluster flavour (S > 0): every share must be resident
+static RowsGeom rows_geometry(int pde, int n, int npar, const Segments &seg, int G, int chunk_override = 0, int S = 0, int C = 0)
 {
-    RowsGeom g = {1, ROWS_THREADS, 0, 0, false};
-    if (Np < 1 || Np > ROWS_MAX_PARAMS) return g;
-    const int nps = (Np + ROWS_M - 1) / ROWS_M;
-    int npsp = 1;
-    while (npsp < nps) npsp <<= 1;
-    g.npsp = npsp; g.rs = ROWS_THREADS / npsp;
+    RowsGeom g = {1, ROWS_THREADS, 0, 0, false, S, C};
+    if (npar < 1 || npar > ROWS_MAX_PARAMS) return g;
+    const int nps = (npar + ROWS_M - 1) / ROWS_M;
+    g.npsp = nps; g.rs = ROWS_THREADS / nps;
     const int narr = pde == PDE_B ? 4 : 3, nvec = pde == PDE_KG ? 2 : 1, nqx = (n + 3) / 4;
     const size_t row_floats = (size_t)narr * nqx * 4 + nvec;
     size_t fl = 0;
@@ -438,7 +443,10 @@ static RowsGeom rows_geometry(int pde, int n, int Np, const Segments &seg, int G
         share = std::max<long long>(4, (share + 3) & ~3LL);
         fl += (size_t)share * row_floats + 4;
     }
-    if (g.rs > 1) fl += (size_t)ROWS_THREADS * ROWS_M * (n + 1);
+    // slice-reduction buffer [rs][npsp * M][ROWS_KC] (rs > 1) and, aliased with it (grid flavour), the staged coefficient
+    // table [n][npsp * M]; cluster flavour: + this CTA's partial sums and its copy of the coefficient table
+    if (S > 0) fl += (g.rs > 1 ? (size_t)ROWS_THREADS * ROWS_M * ROWS_KC : 0) + (((size_t)nps * ROWS_M * (n + 1) + 3) & ~(size_t)3) + (size_t)nps * ROWS_M * n;
+    else fl += std::max(g.rs > 1 ? (size_t)ROWS_THREADS * ROWS_M * ROWS_KC : 0, (size_t)nps * ROWS_M * n);
     const size_t budget = (size_t)(220 * 1024) / sizeof(float);
     if (fl + 64 * row_floats > budget) return g;
     long long share0 = (seg.rows[0] + G - 1) / G + 1;
@@ -446,27 +454,39 @@ static RowsGeom rows_geometry(int pde, int n, int Np, const Segments &seg, int G
     const long long cap_total = (long long)((budget - fl) / row_floats) & ~3LL;
     int nbuf = 1;
     if (share0 <= cap_total) g.chunk_rows = (int)share0;                // the CTA's residual share stays resident
+    else if (S > 0) return g;
     else { g.chunk_rows = (int)std::min<long long>((cap_total / 2) & ~3LL, 512); nbuf = 2; }   // streamed through a double buffer
-    if (chunk_override > 0 && ((chunk_override + 3) & ~3) < g.chunk_rows) { g.chunk_rows = std::max(4, (chunk_override + 3) & ~3); nbuf = 2; }   // tests: force streaming
+    if (S == 0 && chunk_override > 0 && ((chunk_override + 3) & ~3) < g.chunk_rows) { g.chunk_rows = std::max(4, (chunk_override + 3) & ~3); nbuf = 2; }   // tests: force streaming
     g.smem = (fl + (size_t)nbuf * g.chunk_rows * row_floats + 8) * sizeof(float);
     g.ok = true;
     return g;
 }
 
-// modelled SMSP cycles per epoch, in the units of item_instr(): FMAs of the T-free formulation + row loads, all parameters
-// on every CTA's share of the rows, plus two grid barriers and the partial-sum traffic
-static double rows_cost(int pde, int n, int Np, const Segments &seg, int G, const RowsGeom &g)
+// modelled SMSP cycles per epoch, in the units of item_instr(): FMAs of the T-free formulation + row loads on every CTA's
+// share of the rows for its parameters, plus the per-epoch exchange (calibrated on B200: the grid flavour pays two grid
+// barriers and a global-memory round trip of the partials, about 9 us; the cluster flavour two cluster barriers and the
+// distributed-shared-memory sums)
+static double rows_cost(int pde, int n, int npar_total, const Segments &seg, int G, const RowsGeom &g)
 {
     const double fma_res = (pde == PDE_B ? 8.0 : 6.0) * n + 14.0, fma_icbc = (pde == PDE_KG ? 4.0 : 2.0) * n + 8.0, fma_bc = (pde == PDE_AC ? 3.0 : 2.0) * n + 6.0;
     double rows_inst = 0.0;
     for (int s = 0; s < seg.nseg; ++s) {
-        const double share = std::ceil((double)seg.rows[s] / G / g.rs);                      // rows per thread
+        const double share = std::ceil(std::ceil((double)seg.rows[s] / G) / g.rs);            // rows per thread
         rows_inst += share * ROWS_M * (s == 0 ? fma_res : (s == 1 ? fma_icbc : fma_bc));
     }
-    const double issue = rows_inst * 2.0 / 0.70;                        // 8 warps = 2 per SMSP, ~70 % issue efficiency
-    const double barriers = 2.0 * 5500.0;                               // two grid barriers, ~2.8 us each at 1.96 GHz
-    const double traffic = 2.0 * (double)Np * (n + 1) * 4.0 * G / kL2BytesPerCycle + (double)G * 30.0;   // partials written + read; G dependent loads
-    return issue + barriers + traffic;
+    const double issue = rows_inst * 2.0 / 0.58;                        // 8 warps = 2 per SMSP, measured issue efficiency of this loop
+    const int passes = (n + 1 + ROWS_KC - 1) / ROWS_KC;
+    const double slices = g.rs > 1 ? passes * (g.rs * 8.0 + 400.0) : 0.0;
+    // measured on B200 (tools/check_rows.py): the cluster flavour costs about 4.5 us per epoch besides the row loops (two
+    // cluster barriers, the distributed-shared-memory sums, the table reload, loop start-up latencies) ...
+    if (g.S > 0) return issue + slices + 7000.0;
+    // ... the grid flavour two grid barriers (about 3.3 us each), the owner phase (G partials per pair, `tpp` lanes per
+    // pair with four loads in flight: ceil(G / (4 tpp)) dependent L2 round trips) and the partial-sum traffic
+    int tpp = 1;
+    while (tpp < 32 && (long long)npar_total * (n + 1) * (tpp * 2) <= (long long)G * ROWS_THREADS) tpp *= 2;
+    const double barriers = 2.0 * 6500.0;
+    const double traffic = 2.0 * (double)npar_total * (n + 1) * 4.0 * G / kL2BytesPerCycle + std::ceil(G / (4.0 * tpp)) * 1500.0 + 2500.0;
+    return issue + slices + barriers + traffic;
 }
 
 static int run_sweep_rows(gptpinn_handle *h, int pde, int n, const Segments &seg, PackJobs &jobs, bool has_fhat,
@@ -494,8 +514,8 @@ static int run_sweep_rows(gptpinn_handle *h, int pde, int n, const Segments &seg
     h->packed_cap = cap_f / sizeof(float);
     if (rc) return rc;
     const int Np = a->Np, NV = n + 1;
-    const size_t pp_b = (size_t)Np * sizeof(float4), cg_b = (((size_t)Np * n * sizeof(float)) + 15) & ~(size_t)15;
-    const size_t part_b = (size_t)G * Np * NV * sizeof(float);
+    const size_t pp_b = (size_t)Np * sizeof(float4), cg_b = (size_t)geo.npsp * ROWS_M * n * sizeof(float);      // [n][npsp * M]
+    const size_t part_b = geo.S > 0 ? 16 : (size_t)G * Np * NV * sizeof(float);
     rc = ensure(&h->rows_ws, &h->rows_cap, pp_b + cg_b + part_b);
     if (rc) return rc;
     std::vector<float4> pp((size_t)Np);
@@ -515,6 +535,7 @@ static int run_sweep_rows(gptpinn_handle *h, int pde, int n, const Segments &seg
     p.nrec = p.rec_every > 0 ? a->epochs / p.rec_every + 1 : 0;
     p.has_fhat = has_fhat ? 1 : 0;
     p.Np = Np; p.npsp = geo.npsp; p.rs = geo.rs;
+    p.S = geo.S; p.C = geo.C;
     p.tpp = 1;
     while (p.tpp < 32 && (long long)Np * NV * (p.tpp * 2) <= (long long)G * ROWS_THREADS) p.tpp *= 2;
     p.pp = (const float4 *)h->rows_ws;
@@ -530,7 +551,7 @@ static int run_sweep_rows(gptpinn_handle *h, int pde, int n, const Segments &seg
     if (info) {
         memset(info, 0, sizeof(*info));
         info->M = ROWS_M; info->SL = geo.npsp; info->W = ROWS_THREADS / 32; info->items = Np; info->groups = Np;
-        info->ctas = G; info->rounds = 1; info->priv = 2; info->K = geo.rs; info->kernels_launched = 2;
+        info->ctas = G; info->rounds = 1; info->priv = geo.S > 0 ? 3 : 2; info->K = geo.S > 0 ? geo.S : geo.rs; info->kernels_launched = 2;
         info->smem_bytes = (int)geo.smem; info->tiles_per_pass = (int)tiles;
     }
     return GPTPINN_OK;
@@ -550,23 +571,52 @@ static int run_sweep(gptpinn_handle *h, int pde, int n, const Segments &seg, Pac
         if (info) memset(info, 0, sizeof(*info));
         return GPTPINN_OK;
     }
-    // row-partitioned kernel: few parameters (<= 1024), no early-exit bound; chosen by cfg_mode 3 or by the cost model
-    if (a->cfg_mode == 3 || (a->cfg_mode == 0 && !a->bound_dev && a->Np <= ROWS_MAX_PARAMS)) {
+    // row-partitioned kernels (sweep_rows.cuh): few parameters, no early-exit bound.  cfg_mode 3 = grid flavour (cooperative
+    // launch, any row count), cfg_mode 4 = cluster flavour (cfg_K = CTAs per cluster, 0 = best), cfg_mode 0 = cheapest of
+    // the work-item plan and the two flavours by the cost model
+    if (a->cfg_mode == 3 || a->cfg_mode == 4 || (a->cfg_mode == 0 && !a->bound_dev && !a->cfg_M && !a->cfg_SL && !a->cfg_W && !a->cfg_K)) {
+        if (a->cfg_mode != 0 && a->bound_dev) return fail(GPTPINN_E_INVALID, "bound_dev (early exit) is not available in the row-partitioned kernels");
         int coop = 0;
         CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-        const RowsGeom geo = rows_geometry(pde, n, a->Np, seg, h->n_sm, a->cfg_mode == 3 ? a->cfg_W : 0);
-        if (a->cfg_mode == 3) {
-            if (a->bound_dev) return fail(GPTPINN_E_INVALID, "bound_dev (early exit) is not available in the row-partitioned kernel");
-            if (!coop || !geo.ok) return fail(GPTPINN_E_UNSUPPORTED, "row-partitioned kernel: needs <= %d parameters, cooperative launch and the boundary rows in shared memory", ROWS_MAX_PARAMS);
-            return run_sweep_rows(h, pde, n, seg, jobs, has_fhat, NR, NI, NB, rows, a, info, geo, h->n_sm, st);
+        RowsGeom best_geo = {1, ROWS_THREADS, 0, 0, false, 0, 0};
+        double best_cost = 1e300;
+        int best_G = 0;
+        if (a->cfg_mode != 4 && coop && a->Np <= ROWS_MAX_PARAMS) {
+            const RowsGeom geo = rows_geometry(pde, n, a->Np, seg, h->n_sm, a->cfg_mode == 3 ? a->cfg_W : 0);
+            if (geo.ok) { best_geo = geo; best_cost = rows_cost(pde, n, a->Np, seg, h->n_sm, geo); best_G = h->n_sm; }
         }
-        if (coop && geo.ok && !a->cfg_M && !a->cfg_SL && !a->cfg_W && !a->cfg_K) {
+        if (a->cfg_mode != 3 && kRowsClusters[pde][n - 1]) {
+            for (int S = 16; S >= 1; S >>= 1) {
+                if (a->cfg_mode == 4 && a->cfg_K > 0 && S != a->cfg_K) continue;
+                int C = std::min(h->n_sm / S, (a->Np + ROWS_M - 1) / ROWS_M);          // at least one parameter set per cluster
+                if (const char *ov = getenv("GPTPINN_ROWS_C")) C = std::max(1, std::min(C, atoi(ov)));   // experiments: fewer clusters
+                if (C < 1) continue;
+                if ((a->Np + C - 1) / C > ROWS_MAX_PARAMS) continue;
+                RowsGeom geo = rows_geometry(pde, n, (a->Np + C - 1) / C, seg, S, 0, S, C);
+                if (!geo.ok) continue;
+                const int fit = kRowsClusters[pde][n - 1](S, geo.smem);                  // co-resident clusters of this shape
+                if (fit < 1) continue;
+                if (fit < C) {
+                    C = fit;
+                    if ((a->Np + C - 1) / C > ROWS_MAX_PARAMS) continue;
+                    geo = rows_geometry(pde, n, (a->Np + C - 1) / C, seg, S, 0, S, C);
+                    if (!geo.ok) continue;
+                }
+                const double cst = rows_cost(pde, n, a->Np, seg, S, geo);
+                if (cst < best_cost) { best_cost = cst; best_geo = geo; best_G = S * C; }
+            }
+        }
+        if (a->cfg_mode != 0) {
+            if (!best_geo.ok) return fail(GPTPINN_E_UNSUPPORTED, "row-partitioned kernel: needs <= %d parameters per CTA, a cooperative / cluster launch and the row shares in shared memory", ROWS_MAX_PARAMS);
+            return run_sweep_rows(h, pde, n, seg, jobs, has_fhat, NR, NI, NB, rows, a, info, best_geo, best_G, st);
+        }
+        if (best_geo.ok) {
             Plan probe;
             std::vector<ParamRow> tmp(rows);
             int rcp = make_plan(tmp, pde, n, h->n_sm, seg.rows, seg.nseg, a, probe);
             if (rcp) return rcp;
-            if (rows_cost(pde, n, a->Np, seg, h->n_sm, geo) < probe.cost)
-                return run_sweep_rows(h, pde, n, seg, jobs, has_fhat, NR, NI, NB, rows, a, info, geo, h->n_sm, st);
+            if (best_cost < probe.cost)
+                return run_sweep_rows(h, pde, n, seg, jobs, has_fhat, NR, NI, NB, rows, a, info, best_geo, best_G, st);
         }
     }
     Plan plan;

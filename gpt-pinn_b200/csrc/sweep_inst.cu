@@ -14,4 +14,8 @@ cudaError_t GP_CAT(sweep_rows_launch_, GP_PDE, GP_N)(const RowsParams &p, int gr
 {
     return rows_launch<GP_PDE, GP_N>(p, grid, smem, st);
 }
+int GP_CAT(sweep_rows_clusters_, GP_PDE, GP_N)(int S, size_t smem)
+{
+    return rows_max_clusters<GP_PDE, GP_N>(S, smem);
+}
 }  // namespace gp

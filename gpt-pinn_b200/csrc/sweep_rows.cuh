@@ -18,6 +18,16 @@
 //     (parameter, component) pair is summed over the CTAs in fixed order by ONE thread of the grid, which also applies
 //     c <- c - lr g and keeps the loss bookkeeping (final, min-prefix, trace) -> grid barrier -> threads reload their c.
 // Results differ from the main kernel only by summation order and the fused T (within the 1e-5 parity tolerance).
+//
+// Two flavours of the per-epoch exchange (template flag CL):
+//   CL = false: one cooperative grid; partials and coefficients go through global memory, two grid barriers per epoch.  Any
+//               row count (the residual share is streamed when it does not fit) -- the 10^6-row test sweep runs here.
+//   CL = true : thread-block CLUSTERS.  The parameters are split over the clusters, the rows over the S CTAs of a cluster
+//               (S <= 16, every share resident in shared memory); per epoch the CTA partials stay in shared memory, one
+//               cluster barrier, every CTA sums its slice of the (parameter, component) pairs over the S partials through
+//               distributed shared memory (fixed order) and PUSHES the updated coefficient into the coefficient table of
+//               all S CTAs, a second cluster barrier.  No global-memory round trip and no grid-wide barrier on the epoch's
+//               critical path: this is what the default-size grids (100..1000 parameters, 2000 epochs of a few us) need.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -30,6 +40,8 @@ namespace cgx = cooperative_groups;
 constexpr int ROWS_THREADS = 256;
 constexpr int ROWS_M = 4;                      // parameters per thread
 constexpr int ROWS_MAX_PARAMS = ROWS_THREADS * ROWS_M;
+constexpr int ROWS_KC = 4;                     // components per pass of the row-slice reduction
+static_assert(ROWS_M == 4, "the coefficient table is read as one float4 per thread and component");
 
 struct RowsParams {
     const float *packed;                       // tile stream of the main kernel (RT_PRIV-row tiles, SlotFloats per tile)
@@ -40,13 +52,14 @@ struct RowsParams {
     int   chunk_rows;                          // residual rows that fit in the streaming buffer (multiple of 4)
     float invR, invI, invB, fac1, fac2, fac3, lr;
     int   epochs, rec_every, nrec, has_fhat;
-    int   Np, npsp, rs;                        // parameters, padded parameter sets (power of two), row slices = 256 / npsp
+    int   Np, npsp, rs;                        // parameters, parameter sets per CTA (<= 256), row slices = 256 / npsp (threads past npsp * rs idle)
+    int   S, C;                                // cluster flavour: CTAs per cluster, clusters (parameters split evenly over them)
     int   tpp;                                 // lanes that share one (parameter, component) pair in the owner phase (power of two <= 32)
     const float4 *pp;                          // [Np] (tp0, tp1, sp0, sp1)
     const float *c0; int c0_per_param;
     float *c_out, *f_out, *m_out, *trace;
     unsigned long long *key_out; const int *key_index;      // fused arg-max key (see SweepParams)
-    float *cglob;                              // [Np][N]   current coefficients
+    float *cglob;                              // [N][npsp * M]  current coefficients, component-major (one float4 = the four parameters of a thread)
     float *partial;                            // [grid][Np][N+1]
 };
 
@@ -106,7 +119,7 @@ __device__ __forceinline__ void rows_ld(const float *blk, int cap, int r, float 
     }
 }
 
-template <int PDE, int N>
+template <int PDE, int N, bool CL>
 __global__ void __launch_bounds__(ROWS_THREADS, 1) sweep_rows_kernel(const RowsParams p)
 {
     using TR = PdeTraits<PDE>;
@@ -115,9 +128,18 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) sweep_rows_kernel(const RowsP
     constexpr int NV = N + 1;
     constexpr int NARR = TR::NARR, NVEC = TR::NVEC;
     cgx::grid_group grid = cgx::this_grid();
+    cgx::cluster_group cluster = cgx::this_cluster();
     extern __shared__ __align__(16) float rsm[];
-    const int b = blockIdx.x, G = gridDim.x, tid = threadIdx.x;
-    const int ps = tid & (p.npsp - 1), rs = tid / p.npsp, RS = p.rs;
+    const int tid = threadIdx.x;
+    // rows are shared out over the G CTAs of the grid (CL: of the cluster); b = this CTA's place among them
+    const int b = CL ? (int)cluster.block_rank() : (int)blockIdx.x, G = CL ? p.S : (int)gridDim.x;
+    // parameters [pbase, pbase + npc) belong to this CTA's cluster (CL) / all parameters to every CTA
+    const int cid = CL ? (int)blockIdx.x / p.S : 0;
+    const int pbase = CL ? (int)(((long long)p.Np * cid) / p.C) : 0;
+    const int npc = CL ? (int)(((long long)p.Np * (cid + 1)) / p.C) - pbase : p.Np;
+    const int ps = tid % p.npsp, RS = p.rs;
+    const bool idle = tid / p.npsp >= RS;                                // threads past npsp * RS take no rows
+    const int rs = idle ? 0 : tid / p.npsp;
 
     // ---- this CTA's share of every segment; shared-memory regions
     int lo[MAX_SEG], hi[MAX_SEG], cap[MAX_SEG];
@@ -126,7 +148,9 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) sweep_rows_kernel(const RowsP
     const int row_floats = NARR * NQX * 4 + NVEC;
     for (int s = 0; s < p.nseg; ++s) {
         rows_share(p.seg_rows[s], b, G, lo[s], hi[s]);
-        int n = hi[s] - lo[s];
+        // the LARGEST share sizes the region: every CTA has the same shared-memory layout (the cluster flavour addresses
+        // the other CTAs' buffers by its own offsets)
+        int n = (p.seg_rows[s] + G - 1) / G;
         const bool streamed = (s == 0 && n > p.chunk_rows);              // residual rows go through a double buffer of chunks
         if (streamed) n = p.chunk_rows;
         cap[s] = (n + 3) & ~3;
@@ -135,7 +159,15 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) sweep_rows_kernel(const RowsP
         off += cap[s] * row_floats * (streamed ? 2 : 1);
         off = (off + 3) & ~3;
     }
-    float *red = rsm + off;                                            // [RS][npsp * M][NV]   (RS > 1 only)
+    float *red = rsm + off;                                            // [RS][npsp * M][ROWS_KC]   (RS > 1 only)
+    float *csm = red;                                                  // [N][npsp * M] staging of the new coefficients (after the owner
+                                                                       // phase; `red` is dead by then, the host sizes the region for both)
+    const int NPP = p.npsp * M;
+    // cluster flavour: this CTA's partial sums [NPP][NV] and its copy of the coefficient table [N][NPP], both reachable by
+    // the other CTAs of the cluster through distributed shared memory
+    float *part = red + (RS > 1 ? (size_t)ROWS_THREADS * M * ROWS_KC : 0);
+    float *ctab = part + (((size_t)NPP * NV + 3) & ~(size_t)3);
+    if constexpr (CL) csm = ctab;
     const int res_rows = hi[0] - lo[0];
     const bool resident = res_rows <= cap[0];
     for (int s = resident ? 0 : 1; s < p.nseg; ++s) rows_load<NARR, NVEC, NQX>(p, s, lo[s], hi[s] - lo[s], cap[s], reg[s]);
@@ -147,8 +179,8 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) sweep_rows_kernel(const RowsP
     bool valid[M];
 #pragma unroll
     for (int m = 0; m < M; ++m) {
-        const int pi = ps * M + m;
-        valid[m] = pi < p.Np;
+        const int pi = pbase + ps * M + m;
+        valid[m] = !idle && ps * M + m < npc;
         const float4 q = valid[m] ? p.pp[pi] : make_float4(0.f, 0.f, 0.f, 0.f);
         tp0[m] = q.x; tp1[m] = q.y; sp0[m] = q.z; sp1[m] = q.w;
 #pragma unroll
@@ -157,6 +189,13 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) sweep_rows_kernel(const RowsP
     const bool has_fhat = p.has_fhat != 0;
     const int Q = p.Np * NV;
     const int gthreads = G * ROWS_THREADS, gtid = b * ROWS_THREADS + tid;
+    if constexpr (CL) {
+        for (int e = tid; e < N * NPP; e += ROWS_THREADS) {
+            const int v = e / NPP, pl = e % NPP;
+            ctab[e] = pl < npc ? (p.c0_per_param ? p.c0[(size_t)(pbase + pl) * N + v] : p.c0[v]) : 0.f;
+        }
+        __syncthreads();
+    }
 
     for (int j = 0; j <= p.epochs; ++j) {
         float lacc[M], lsum[M];
@@ -188,7 +227,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) sweep_rows_kernel(const RowsP
             const float *A0 = base, *A1 = A0 + NQX * cap[0] * 4, *A2 = A1 + NQX * cap[0] * 4;
             const float *A3 = A2 + NQX * cap[0] * 4;                    // Burgers only
             const float *V0 = base + NARR * NQX * cap[0] * 4, *V1 = V0 + cap[0];
-            for (int r = rs; r < nr; r += RS) {
+            for (int r = idle ? nr : rs; r < nr; r += RS) {
                 float Pa[4 * NQX], Pb[4 * NQX], Pv[4 * NQX];
                 rows_ld<NQX>(A0, cap[0], r, Pa);                         // P_tt (KG) / P_t (B, AC)
                 rows_ld<NQX>(A1, cap[0], r, Pb);                         // P_xx
@@ -250,7 +289,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) sweep_rows_kernel(const RowsP
             const int nr = hi[1] - lo[1];
             const float *A0 = reg[1], *A1 = A0 + NQX * cap[1] * 4;
             const float *V0 = reg[1] + NARR * NQX * cap[1] * 4, *V1 = V0 + cap[1];
-            for (int r = rs; r < nr; r += RS) {
+            for (int r = idle ? nr : rs; r < nr; r += RS) {
                 float Av[4 * NQX];
                 rows_ld<NQX>(A0, cap[1], r, Av);
                 const float tg = V0[r];
@@ -292,7 +331,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) sweep_rows_kernel(const RowsP
             const int nr = hi[s] - lo[s];
             const float *A0 = reg[s], *A1 = A0 + NQX * cap[s] * 4, *A2 = A1 + NQX * cap[s] * 4;
             const float *V0 = reg[s] + NARR * NQX * cap[s] * 4;
-            for (int r = rs; r < nr; r += RS) {
+            for (int r = idle ? nr : rs; r < nr; r += RS) {
                 float Av[4 * NQX];
                 rows_ld<NQX>(A0, cap[s], r, Av);
                 if constexpr (PDE == PDE_AC) {                       // periodic: (P_ub c - P_lb c) * P_diff
@@ -329,8 +368,10 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) sweep_rows_kernel(const RowsP
 #pragma unroll
         for (int m = 0; m < M; ++m) lsum[m] = fmaf(lacc[m], p.invB, lsum[m]);
 
-        // ------------------------------ CTA partial: sum over the row slices (fixed order), write [Np][NV] to global
-        float *mine = p.partial + (size_t)b * Q;
+        // ------------------------------ CTA partial: sum over the row slices (fixed order) -> [parameters][NV], to global
+        // memory (grid flavour) or to this CTA's shared memory (cluster flavour)
+        const int QL = CL ? npc * NV : Q;                                 // (parameter, component) pairs this CTA works on
+        float *mine = CL ? part : p.partial + (size_t)b * Q;
         if (RS == 1) {
 #pragma unroll
             for (int m = 0; m < M; ++m)
@@ -341,28 +382,87 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) sweep_rows_kernel(const RowsP
                     dst[N] = lsum[m];
                 }
         } else {
-            const int plane = p.npsp * M * NV;
-            float *my = red + (size_t)rs * plane + (size_t)ps * M * NV;
+            // the RS row slices of a parameter set are summed through shared memory, ROWS_KC components per pass
+            // (buffer [RS][npsp * M][ROWS_KC]: 16 KB instead of [RS][npsp * M][NV])
+            constexpr int KC = ROWS_KC;
+            const int plane = p.npsp * M * KC;
 #pragma unroll
-            for (int m = 0; m < M; ++m) {
+            for (int k0 = 0; k0 < NV; k0 += KC) {
+                if (!idle) {
+                    float *my = red + (size_t)rs * plane + (size_t)ps * M * KC;
 #pragma unroll
-                for (int k = 0; k < N; ++k) my[m * NV + k] = g[m][k];
-                my[m * NV + N] = lsum[m];
-            }
-            __syncthreads();
-            for (int e = tid; e < Q; e += ROWS_THREADS) {
-                float s = 0.f;
-                for (int q = 0; q < RS; ++q) s += red[(size_t)q * plane + e];
-                mine[e] = s;
+                    for (int m = 0; m < M; ++m)
+#pragma unroll
+                        for (int kk = 0; kk < KC; ++kk)
+                            if (k0 + kk < NV) my[m * KC + kk] = (k0 + kk < N) ? g[m][(k0 + kk < N) ? k0 + kk : 0] : lsum[m];
+                }
+                __syncthreads();
+                const int kc = (NV - k0 < KC) ? NV - k0 : KC;
+                for (int e = tid; e < (QL / NV) * KC; e += ROWS_THREADS) {
+                    const int pl = e / KC, kk = e % KC;
+                    if (kk < kc) {
+                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                        int q = 0;
+                        for (; q + 3 < RS; q += 4) {
+                            s0 += red[(size_t)q * plane + e]; s1 += red[(size_t)(q + 1) * plane + e];
+                            s2 += red[(size_t)(q + 2) * plane + e]; s3 += red[(size_t)(q + 3) * plane + e];
+                        }
+                        for (; q < RS; ++q) s0 += red[(size_t)q * plane + e];
+                        mine[(size_t)pl * NV + k0 + kk] = (s0 + s1) + (s2 + s3);
+                    }
+                }
+                __syncthreads();
             }
         }
+        const bool last = (j == p.epochs);
+        const bool rec = p.trace != nullptr && p.rec_every > 0 && (j % p.rec_every) == 0;
+        // loss bookkeeping of the owner of pair (pi, N): trace, final loss + arg-max key, running minimum of the earlier losses
+        auto keep_loss = [&](int pi, float s) {
+            if (rec) p.trace[(size_t)pi * p.nrec + j / p.rec_every] = s;
+            if (last) {
+                p.f_out[pi] = s;
+                if (p.epochs == 0) p.m_out[pi] = __int_as_float(0x7f800000);
+                if (p.key_out != nullptr && s > 0.f)
+                    atomicMax(p.key_out, ((unsigned long long)__float_as_uint(s) << 32) |
+                                             (unsigned long long)(0xFFFFFFFFu - (unsigned)(p.key_index ? p.key_index[pi] : pi)));
+            } else {
+                const float mprev = (j == 0) ? __int_as_float(0x7f800000) : __ldcg(p.m_out + pi);
+                p.m_out[pi] = (s < mprev) ? s : mprev;
+            }
+        };
+        if constexpr (CL) {
+            // ------------------------------ cluster exchange: the S partials are summed through distributed shared memory
+            // (CTA b owns the pairs e = b (mod S); fixed order q = 0..S-1 => deterministic), the owner pushes the new
+            // coefficient into the table of every CTA of the cluster
+            cluster.sync();
+            const int S = p.S;
+            // CTA b owns the pairs e = b (mod S).  One thread per (owned pair, source CTA): S consecutive lanes fetch the S
+            // partials of a pair in one round trip, a butterfly over those lanes (fixed tree => deterministic, every lane
+            // ends with the same bits) sums them, and lane q of the group pushes the new coefficient to CTA q.
+            const int owned = (QL - b + S - 1) / S;                      // pairs b, b + S, ... < QL
+            const int tasks = ((owned * S + 31) / 32) * 32;              // warp-uniform trip count (full-mask shuffles)
+            for (int t = tid; t < tasks; t += ROWS_THREADS) {
+                const int ei = t / S, q = t % S, e = b + S * ei;
+                const bool act = ei < owned;
+                float sum = act ? cluster.map_shared_rank(part, q)[e] : 0.f;
+                for (int off = S >> 1; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+                if (act) {
+                    const int pl = e / NV, v = e % NV, pi = pbase + pl;
+                    if (v < N) {
+                        const float cur = ctab[v * NPP + pl];
+                        if (last) { if (q == 0 && p.c_out) p.c_out[(size_t)pi * N + v] = cur; }
+                        else cluster.map_shared_rank(ctab, q)[v * NPP + pl] = __fsub_rn(cur, __fmul_rn(p.lr, sum));
+                    } else if (q == 0) keep_loss(pi, sum);
+                }
+            }
+            cluster.sync();                                              // tables complete; partials free for the next epoch
+            if (last) break;
+        } else {
         __threadfence();
         grid.sync();
 
         // ------------------------------ owners: `tpp` lanes of the grid per (parameter, component) pair sum the G CTA
         // partials (strided over the CTAs, four loads in flight per lane, fixed combination order => deterministic)
-        const bool last = (j == p.epochs);
-        const bool rec = p.trace != nullptr && p.rec_every > 0 && (j % p.rec_every) == 0;
         {
             const int tpp = p.tpp, ppw = 32 / tpp;                       // pairs per warp and step
             const int lane = tid & 31, sub = lane & (tpp - 1);
@@ -385,51 +485,80 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) sweep_rows_kernel(const RowsP
                 if (act && sub == 0) {
                     const int pi = e / NV, v = e % NV;
                     if (v < N) {
-                        const float cur = (j == 0) ? (p.c0_per_param ? p.c0[(size_t)pi * N + v] : p.c0[v]) : __ldcg(p.cglob + (size_t)pi * N + v);
+                        const float cur = (j == 0) ? (p.c0_per_param ? p.c0[(size_t)pi * N + v] : p.c0[v]) : __ldcg(p.cglob + (size_t)v * NPP + pi);
                         if (last) { if (p.c_out) p.c_out[(size_t)pi * N + v] = cur; }
-                        else p.cglob[(size_t)pi * N + v] = __fsub_rn(cur, __fmul_rn(p.lr, s));
-                    } else {
-                        if (rec) p.trace[(size_t)pi * p.nrec + j / p.rec_every] = s;
-                        if (last) {
-                            p.f_out[pi] = s;
-                            if (p.epochs == 0) p.m_out[pi] = __int_as_float(0x7f800000);
-                            if (p.key_out != nullptr && s > 0.f)
-                                atomicMax(p.key_out, ((unsigned long long)__float_as_uint(s) << 32) |
-                                                         (unsigned long long)(0xFFFFFFFFu - (unsigned)(p.key_index ? p.key_index[pi] : pi)));
-                        } else {
-                            const float mprev = (j == 0) ? __int_as_float(0x7f800000) : __ldcg(p.m_out + pi);
-                            p.m_out[pi] = (s < mprev) ? s : mprev;
-                        }
-                    }
+                        else p.cglob[(size_t)v * NPP + pi] = __fsub_rn(cur, __fmul_rn(p.lr, s));
+                    } else keep_loss(pi, s);
                 }
             }
         }
         if (last) break;
         __threadfence();
         grid.sync();
+        }
+        // every CTA needs every coefficient: one coalesced copy of the table into shared memory (each float requested once per
+        // CTA -- 148 x 256 threads reading their own strided scalars made the few L2 lines of the table a hot spot), then one
+        // LDS.128 per component gives a thread the values of its four parameters
+        if constexpr (!CL) {
+            for (int e = tid; e < N * NPP / 4; e += ROWS_THREADS)
+                reinterpret_cast<float4 *>(csm)[e] = __ldcg(reinterpret_cast<const float4 *>(p.cglob) + e);
+            __syncthreads();
+        }
 #pragma unroll
-        for (int m = 0; m < M; ++m)
-            if (valid[m]) {
-                const float *src = p.cglob + (size_t)(ps * M + m) * N;
-#pragma unroll
-                for (int k = 0; k < N; ++k) c[m][k] = __ldcg(src + k);
-            }
+        for (int k = 0; k < N; ++k) {
+            const float4 v = *reinterpret_cast<const float4 *>(csm + k * NPP + ps * M);
+            c[0][k] = valid[0] ? v.x : 0.f; c[1][k] = valid[1] ? v.y : 0.f; c[2][k] = valid[2] ? v.z : 0.f; c[3][k] = valid[3] ? v.w : 0.f;
+        }
+        if constexpr (!CL) __syncthreads();                             // csm aliases red: the next epoch's partial sums overwrite it
     }
 }
-
-struct RowsLaunch { int grid; size_t smem; };
 
 template <int PDE, int N>
 cudaError_t rows_launch(const RowsParams &p, int grid, size_t smem, cudaStream_t st)
 {
-    auto kern = sweep_rows_kernel<PDE, N>;
+    RowsParams pp = p;
+    if (p.S > 0) {                                                       // cluster flavour: grid = C clusters of S CTAs
+        auto kern = sweep_rows_kernel<PDE, N, true>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (p.S > 8) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e != cudaSuccess) return e;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(ROWS_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = p.S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kern, pp);
+    }
+    auto kern = sweep_rows_kernel<PDE, N, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    RowsParams pp = p;
     void *args[] = {&pp};
     return cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(ROWS_THREADS), args, smem, st);
 }
 
+// how many clusters of S CTAs with `smem` bytes each can be co-resident (0 if the shape cannot launch)
+template <int PDE, int N>
+int rows_max_clusters(int S, size_t smem)
+{
+    auto kern = sweep_rows_kernel<PDE, N, true>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (S > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(S); cfg.blockDim = dim3(ROWS_THREADS); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
 typedef cudaError_t (*rows_launch_fn)(const RowsParams &p, int grid, size_t smem, cudaStream_t st);
+typedef int (*rows_clusters_fn)(int S, size_t smem);
 
 }  // namespace gp

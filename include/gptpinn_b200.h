@@ -118,12 +118,16 @@ typedef struct {
     /* tuning override, 0 = let the library choose: parameters per thread (M), sibling lanes
      * per warp (SL, power of two <= 32), warps per CTA (W).                                   */
     int           cfg_M, cfg_SL, cfg_W;
-    int           cfg_mode;    /* 0 = auto, 1 = shared-ring kernel, 2 = private-ring kernel, 3 = row-partitioned kernel
-                                * (few parameters: rows split over all CTAs of a cooperative grid, every CTA processes
-                                * every parameter, per-epoch reduction through global memory; needs Np <= 1024, no
-                                * bound_dev; with cfg_mode 3, cfg_W > 0 caps the residual rows per streaming chunk)      */
+    int           cfg_mode;    /* 0 = auto, 1 = shared-ring kernel, 2 = private-ring kernel, 3 = row-partitioned kernel,
+                                * grid flavour (few parameters: rows split over all CTAs of a cooperative grid, every CTA
+                                * processes every parameter, per-epoch reduction through global memory; needs Np <= 1024,
+                                * no bound_dev; cfg_W > 0 caps the residual rows per streaming chunk), 4 = row-partitioned
+                                * kernel, cluster flavour (parameters split over thread-block clusters, rows over the CTAs
+                                * of a cluster, per-epoch reduction through distributed shared memory; row shares must fit
+                                * in shared memory, no bound_dev; cfg_K = CTAs per cluster, 0 = best)                     */
     int           cfg_K;       /* 0 = auto; private-ring kernel: warps that team up on one work item
-                                * (1, 2, 4 or 8): they split the tiles of a pass and sum their gradients   */
+                                * (1, 2, 4 or 8): they split the tiles of a pass and sum their gradients;
+                                * cfg_mode 4: CTAs per cluster (1, 2, 4, 8 or 16)                           */
     /* Optional early exit with the reference's semantics (KG_train.py:31-33 `if loss < largest_loss: break`):
      * bound_dev[p] must be <= the running maximum the reference's sequential loop holds when it reaches grid
      * row p (e.g. the max of min(f, m) over already finished rows p' < p).  Row p then stops at the
@@ -149,8 +153,9 @@ typedef struct {
     int   kernels_launched;    /* sweep + pack kernels enqueued by this call                   */
     int   smem_bytes;
     int   tiles_per_pass;
-    int   priv;                /* 1 = private-ring kernel (dynamic tickets), 0 = shared ring    */
-    int   K;                   /* warps per team (private-ring kernel), else 1                  */
+    int   priv;                /* 0 = shared ring, 1 = private-ring kernel (dynamic tickets), 2 = row-partitioned kernel
+                                * (grid flavour), 3 = row-partitioned kernel (cluster flavour)    */
+    int   K;                   /* warps per team (private-ring kernel); row slices per CTA (priv 2); CTAs per cluster (priv 3) */
 } gptpinn_sweep_info;
 
 int  gptpinn_version(void);
