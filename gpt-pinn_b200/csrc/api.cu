@@ -70,6 +70,7 @@ struct gptpinn_handle {
     unsigned int *counter = nullptr;                      // work-item ticket
     void *train_ws = nullptr;  size_t train_cap = 0;      // packed params | adam m | adam v | partials | status | stop
     void *rows_ws = nullptr;   size_t rows_cap = 0;       // row-partitioned sweep: parameter table | coefficients | CTA partials
+    void *tglob = nullptr;     size_t tglob_cap = 0;      // precomputed T arrays of the (alpha, beta) groups | their (tp0, tp1) table
 };
 
 static int ensure(void **ptr, size_t *cap, size_t need)
@@ -113,6 +114,7 @@ extern "C" int gptpinn_destroy(gptpinn_handle *h)
     if (h->counter) cudaFree(h->counter);
     if (h->train_ws) cudaFree(h->train_ws);
     if (h->rows_ws) cudaFree(h->rows_ws);
+    if (h->tglob) cudaFree(h->tglob);
     delete h;
     return GPTPINN_OK;
 }
@@ -394,6 +396,7 @@ static int make_plan(std::vector<ParamRow> &rows, int pde, int n, int n_sm, cons
         const int base = gstart[c.g] + c.s0;
         ItemDesc it;
         memset(&it, 0, sizeof(it));
+        it.t_slot = -1;
         it.tp0 = rows[base].tp0; it.tp1 = rows[base].tp1;
         it.sib_start = (int)plan.sibs.size();
         it.sib_count = c.cnt;
@@ -652,10 +655,48 @@ static int run_sweep(gptpinn_handle *h, int pde, int n, const Segments &seg, Pac
     rc = ensure(&h->sibs, &h->sibs_cap, plan.sibs.size() * sizeof(SibDesc));
     if (rc) return rc;
 
+    // ---- precomputed T: every group that has a wide work item (T block path of the private-ring kernel) gets its T array
+    //      built once per launch in global memory; the kernel then fetches T tiles instead of rebuilding them per tile and
+    //      epoch.  Skipped (in-kernel build) when the arrays exceed the memory budget or f_hat is non-zero.
+    std::vector<float2> tgroups;
+    const long long tt = (long long)(n / 4 + 1) * 4 * RT, t_stride = (long long)p.ntile[0] * tt;
+    if (plan.priv && !has_fhat && !getenv("GPTPINN_NO_TGLOB")) {
+        std::map<uint64_t, int> slot_of;
+        for (ItemDesc &it : plan.items) {
+            if (it.SL <= GP_REGT_MAX_SL) continue;
+            uint32_t a_, b_;
+            memcpy(&a_, &it.tp0, 4); memcpy(&b_, &it.tp1, 4);
+            const uint64_t key = ((uint64_t)a_ << 32) | b_;
+            auto f = slot_of.find(key);
+            if (f == slot_of.end()) { f = slot_of.emplace(key, (int)tgroups.size()).first; tgroups.push_back(make_float2(it.tp0, it.tp1)); }
+            it.t_slot = f->second;
+        }
+        size_t budget_mb = 8192;
+        if (const char *ev = getenv("GPTPINN_TGLOB_MB")) budget_mb = (size_t)std::max(0, atoi(ev));
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const size_t need = (size_t)tgroups.size() * (size_t)t_stride * sizeof(float) + tgroups.size() * sizeof(float2) + 256;
+        const size_t avail = h->tglob_cap + free_b / 2;                          // never take more than half of what is free
+        if (tgroups.empty() || need > budget_mb * 1024 * 1024 || need + need / 4 > avail) {
+            for (ItemDesc &it : plan.items) it.t_slot = -1;
+            tgroups.clear();
+        } else {
+            rc = ensure(&h->tglob, &h->tglob_cap, need);
+            if (rc) return rc;
+        }
+    }
+
     if (!h->counter) CUDA_TRY(cudaMalloc((void **)&h->counter, sizeof(unsigned int)));
     CUDA_TRY(cudaMemsetAsync(h->counter, 0, sizeof(unsigned int), st));
     CUDA_TRY(cudaMemsetAsync(h->packed, 0, (size_t)tiles * slot * sizeof(float), st));
     CUDA_TRY(launch_pack(jobs, h->packed, max_rows, st));
+    if (!tgroups.empty()) {
+        float2 *gtab = (float2 *)((char *)h->tglob + (((size_t)tgroups.size() * (size_t)t_stride * sizeof(float) + 255) & ~(size_t)255));
+        CUDA_TRY(cudaMemcpyAsync(gtab, tgroups.data(), tgroups.size() * sizeof(float2), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(launch_build_t(h->packed, slot, RT, pde == PDE_B ? 4 : 3, pde, n, p.ntile[0], gtab, (int)tgroups.size(), (float *)h->tglob, t_stride, st));
+        p.tglob = (const float *)h->tglob;
+        p.t_stride = t_stride;
+    }
     CUDA_TRY(cudaMemcpyAsync(h->items, plan.items.data(), plan.items.size() * sizeof(ItemDesc), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(h->sibs, plan.sibs.data(), plan.sibs.size() * sizeof(SibDesc), cudaMemcpyHostToDevice, st));
     // pageable sources: the copies above have consumed the host vectors when the calls return
@@ -694,7 +735,8 @@ static int run_sweep(gptpinn_handle *h, int pde, int n, const Segments &seg, Pac
     if (p.n_items > 0) CUDA_TRY(fn(p, plan.M, plan.priv, plan.ctas, smem, st));
     if (info) {
         info->M = plan.M; info->SL = plan.SL; info->W = plan.W; info->items = p.n_items; info->groups = plan.groups;
-        info->ctas = plan.ctas; info->rounds = plan.rounds; info->priv = plan.priv; info->K = plan.priv ? plan.K : 1; info->kernels_launched = p.n_items > 0 ? 2 : 1;
+        info->ctas = plan.ctas; info->rounds = plan.rounds; info->priv = plan.priv; info->K = plan.priv ? plan.K : 1;
+        info->kernels_launched = (p.n_items > 0 ? 2 : 1) + (tgroups.empty() ? 0 : 1);
         info->smem_bytes = (int)smem; info->tiles_per_pass = (int)tiles;
     }
     return GPTPINN_OK;

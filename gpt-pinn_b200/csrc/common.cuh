@@ -54,7 +54,9 @@ struct ItemDesc {          // one warp work item: a set of parameters that share
     int   sib_start;       // first sibling in SibDesc[]
     int   sib_count;       // 1 .. SL*M
     int   SL;              // sibling lanes of this item (power of two); row slices RL = 32/SL
-    int   pad[3];
+    int   t_slot;          // private-ring kernels: index of the group's precomputed T array in SweepParams::tglob, or -1
+                           // (build T in shared memory / in registers from the staged P-derivative tiles)
+    int   pad[2];
 };
 struct SibDesc {
     float sp0, sp1;        // KG: gamma, 2*gamma  B: 0,0        AC: eps, 3*eps
@@ -83,6 +85,8 @@ struct SweepParams {
     const float   *bound;            // private-ring kernels: [Np] per-parameter early-exit bound B_p <= L_seq(p), or nullptr
     unsigned long long *key_out;     // optional: atomicMax of (float_bits(final loss) << 32) | (0xFFFFFFFF - global index) over all rows
     const int     *key_index;        // optional [Np]: global grid index of each row (nullptr: the row number)
+    const float   *tglob;            // private-ring kernels: precomputed T arrays, [t_slot][residual tile][NQT][RT][4] (see build_t_kernel)
+    long long      t_stride;         // floats per T array (= ntile[0] * NQT * 4 * RT)
     int            K;                // private-ring kernels: warps per team (power of two dividing W); a team shares one
                                      // work item, its warps take every K-th tile and sum their gradients once per epoch
 };
@@ -127,6 +131,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// the same for data that is read once and should not displace the reused stream in L2 (evict-first cache hint)
+__device__ __forceinline__ void bulk_g2s_stream(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
 
 }  // namespace gp

@@ -33,6 +33,9 @@ namespace cg = cooperative_groups;
 #ifndef GP_PINN_UNROLL
 #define GP_PINN_UNROLL 1
 #endif
+#ifndef GP_PINN_MINB
+#define GP_PINN_MINB 2                // resident CTAs per SM the register allocation aims at
+#endif
 
 namespace gp {
 
@@ -81,7 +84,7 @@ __device__ __forceinline__ void act_backward(int act, const float (&z)[CH], cons
 
 // WMAX: widest hidden layer (all hidden layers are padded to it), NH: hidden layers (KG 2, Burgers 4)
 template <int WMAX, int NH>
-__global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d, const PinnBatch bt)
+__global__ void __launch_bounds__(NG * 32, GP_PINN_MINB) pinn_train_kernel(const PinnDesc d, const PinnBatch bt)
 {
     // this CTA's training: group `tr` of the grid, local CTA index `lb`; CTAs beyond n * group only keep the barriers
     const int gsz = bt.group;
@@ -99,10 +102,15 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) float smem[];
     const int P = d.n_params;
-    const int P4 = (P + 3) & ~3;
-    float *w_s = smem;                                       // [P]   packed parameters (W row-major [out][in], then b, per layer)
-    float *g_s = w_s + P4;                                   // [P]   this block's gradient partial
-    float *wt_s = g_s + P4;                                  // [NH-1][WMAX][NG][GJP]  hidden->hidden weights, transposed + padded:  wt[l][i][jg][jj] = W[jg*GJ+jj][i]
+    // Shared copies hold everything EXCEPT the hidden->hidden matrices: those live in the padded wt / wp copies (weights) and
+    // in the wacc register tiles (gradients, combined through the staging buffer after the tile loop).  This keeps a CTA at
+    // ~71 KB for the KG network, so three CTAs fit an SM (361 point tiles of the default KG problem in ONE round of 444).
+    int PC = 0;
+    for (int l = 0; l <= NH; ++l) PC += ((l == 0 || l == NH) ? d.layers[l] * d.layers[l + 1] : 0) + d.layers[l + 1];
+    const int PC4 = (PC + 3) & ~3;
+    float *w_s = smem;                                       // [PC]  first / last matrix and all biases, compact (cw / cb offsets)
+    float *g_s = w_s + PC4;                                  // [PC]  this block's gradient partial of the same entries
+    float *wt_s = g_s + PC4;                                 // [NH-1][WMAX][NG][GJP]  hidden->hidden weights, transposed + padded:  wt[l][i][jg][jj] = W[jg*GJ+jj][i]
     float *wp_s = wt_s + (NH - 1) * WMAX * NG * GJP;         // [NH-1][WMAX][NG][GJP]  same weights, row-major + padded:          wp[l][j][ig][ii] = W[j][ig*GJ+ii]
     float *A_s = wp_s + (NH - 1) * WMAX * NG * GJP;          // [WMAX][CH][PT]
     float *B_s = A_s + STG;                                  // [WMAX][CH][PT]
@@ -111,13 +119,16 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
     const int j0 = warp * GJ;                                // first neuron owned by this thread in every hidden layer
     const int tjg = lane / TIG, tig = lane % TIG;
 
-    int woff[NH + 1], boff[NH + 1];
+    int woff[NH + 1], boff[NH + 1];                          // offsets in the packed parameter vector
+    int cw[NH + 1], cb[NH + 1];                              // offsets in the compact shared copies (cw of a hidden->hidden map unused)
     {
-        int off = 0;
+        int off = 0, coff = 0;
 #pragma unroll
         for (int l = 0; l <= NH; ++l) {
             woff[l] = off; off += d.layers[l] * d.layers[l + 1];
             boff[l] = off; off += d.layers[l + 1];
+            cw[l] = coff; if (l == 0 || l == NH) coff += d.layers[l] * d.layers[l + 1];
+            cb[l] = coff; coff += d.layers[l + 1];
         }
     }
     const int tilesR = (d.NR + PT - 1) / PT, tilesI = (d.NI + PT - 1) / PT, tilesB = (d.NB + PT - 1) / PT;
@@ -126,10 +137,15 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
     for (int epoch = 1; epoch <= d.epochs; ++epoch) {
       if (!done) {
         // -------------------------------------------------------------- phase 1
-        for (int i = threadIdx.x; i < P; i += blockDim.x) { w_s[i] = T.params[i]; g_s[i] = 0.f; }
-        __syncthreads();
-        for (int l = 1; l < NH; ++l) {                       // padded copies of the hidden->hidden matrices
-            const float *W = w_s + woff[l];
+#pragma unroll
+        for (int l = 0; l <= NH; ++l) {
+            const int nw = (l == 0 || l == NH) ? d.layers[l] * d.layers[l + 1] : 0, nb = d.layers[l + 1];
+            for (int i = threadIdx.x; i < nw; i += blockDim.x) w_s[cw[l] + i] = T.params[woff[l] + i];
+            for (int i = threadIdx.x; i < nb; i += blockDim.x) w_s[cb[l] + i] = T.params[boff[l] + i];
+        }
+        for (int i = threadIdx.x; i < PC; i += blockDim.x) g_s[i] = 0.f;
+        for (int l = 1; l < NH; ++l) {                       // padded copies of the hidden->hidden matrices (from global / L2)
+            const float *W = T.params + woff[l];
             const int wi = d.layers[l], wo = d.layers[l + 1];
             float *wt = wt_s + (l - 1) * WMAX * NG * GJP, *wp = wp_s + (l - 1) * WMAX * NG * GJP;
             for (int e = threadIdx.x; e < WMAX * NG * GJP; e += blockDim.x) {
@@ -162,7 +178,7 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
             // ================================ forward ================================
             float z[NH][CH][GJ];                      // pre-activations of this thread's neurons, every hidden layer
             {
-                const float *W = w_s + woff[0], *Bv = w_s + boff[0];       // layer 0: inputs (x, t), channels known in closed form
+                const float *W = w_s + cw[0], *Bv = w_s + cb[0];       // layer 0: inputs (x, t), channels known in closed form
 #pragma unroll
                 for (int jj = 0; jj < GJ; ++jj) {
                     const int j = j0 + jj;
@@ -189,7 +205,7 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
                 if (l < NH - 1) {
                     // z_{l+1}[c][j] = b[j] + sum_i W[j][i] a_l[c][i]   (weights as warp-wide broadcasts)
                     const float *wt = wt_s + l * WMAX * NG * GJP + warp * GJP;
-                    const float *Bv = w_s + boff[l + 1];
+                    const float *Bv = w_s + cb[l + 1];
 #pragma unroll
                     for (int jj = 0; jj < GJ; ++jj) {
                         z[l + 1][0][jj] = (j0 + jj) < d.layers[l + 2] ? Bv[j0 + jj] : 0.f;
@@ -219,7 +235,7 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
             // output layer (one linear unit): partial over the thread's neurons, then over the four warps
             float u[CH];
             {
-                const float *W = w_s + woff[NH];
+                const float *W = w_s + cw[NH];
                 float pu[CH] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int jj = 0; jj < GJ; ++jj) {
@@ -232,7 +248,7 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
                 __syncthreads();
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
-                    float s = c == 0 ? w_s[boff[NH]] : 0.f;
+                    float s = c == 0 ? w_s[cb[NH]] : 0.f;
 #pragma unroll
                     for (int g = 0; g < NG; ++g) s += U_s[(g * CH + c) * PT + lane];
                     u[c] = s;
@@ -272,7 +288,7 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
             // output layer: Wbar_out[j] += sum_{c,p} ub_c a_{NH-1}[c][j];  bbar_out += sum_p ub_v;  abar[c][j] = W_out[j] ub_c
             float ab[CH][GJ];                         // adjoint of the activations, then of the pre-activations (in place)
             {
-                const float *W = w_s + woff[NH];
+                const float *W = w_s + cw[NH];
 #pragma unroll
                 for (int jj = 0; jj < GJ; ++jj) {
                     const bool ok = (j0 + jj) < d.layers[NH];
@@ -280,7 +296,7 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
 #pragma unroll
                     for (int c = 0; c < CH; ++c) s = fmaf(ub[c], A_s[(j0 + jj) * NS + c * PT + lane], s);
                     for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-                    if (lane == 0 && ok) g_s[woff[NH] + j0 + jj] += s;
+                    if (lane == 0 && ok) g_s[cw[NH] + j0 + jj] += s;
                     const float wv = ok ? W[j0 + jj] : 0.f;
 #pragma unroll
                     for (int c = 0; c < CH; ++c) ab[c][jj] = wv * ub[c];
@@ -288,7 +304,7 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
                 if (warp == 0) {
                     float s = ub[0];
                     for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-                    if (lane == 0) g_s[boff[NH]] += s;
+                    if (lane == 0) g_s[cb[NH]] += s;
                 }
             }
             __syncthreads();                          // all reads of A (activations of the last hidden layer) are done
@@ -309,7 +325,7 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
                 for (int jj = 0; jj < GJ; ++jj) {
                     float s = ab[0][jj];
                     for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-                    if (lane == 0 && (j0 + jj) < d.layers[l + 1]) g_s[boff[l] + j0 + jj] += s;
+                    if (lane == 0 && (j0 + jj) < d.layers[l + 1]) g_s[cb[l] + j0 + jj] += s;
                 }
                 if (l == 0) {
                     // first linear map: inputs (x, t) with channels (x,1,0,0,0) and (t,0,1,0,0)
@@ -321,8 +337,8 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
                             st += __shfl_xor_sync(0xffffffffu, st, off);
                         }
                         if (lane == 0 && (j0 + jj) < d.layers[1]) {
-                            g_s[woff[0] + (j0 + jj) * 2] += sx;
-                            g_s[woff[0] + (j0 + jj) * 2 + 1] += st;
+                            g_s[cw[0] + (j0 + jj) * 2] += sx;
+                            g_s[cw[0] + (j0 + jj) * 2 + 1] += st;
                         }
                     }
                 } else {
@@ -384,7 +400,11 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
             }
         }   // tiles
 
-        // ---- combine the four warps' weight-gradient tiles (K split) into the block partial, fixed order
+        // ---- combine the four warps' weight-gradient tiles (K split), fixed order, in the staging buffer A (free after
+        //      the tile loop), layer l at A_s[l * WMAX * WMAX + j * wi + i]
+        __syncthreads();
+        for (int i = threadIdx.x; i < (NH - 1) * WMAX * WMAX; i += blockDim.x) A_s[i] = 0.f;
+        __syncthreads();
         for (int w = 0; w < NG; ++w) {
             if (warp == w) {
 #pragma unroll
@@ -395,7 +415,7 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
 #pragma unroll
                         for (int b = 0; b < TI; ++b) {
                             const int j = tjg * TJ + a, i = tig * TI + b;
-                            if (j < wo && i < wi) g_s[woff[l + 1] + j * wi + i] += wacc[l][a][b];
+                            if (j < wo && i < wi) A_s[l * WMAX * WMAX + j * wi + i] += wacc[l][a][b];
                         }
                 }
             }
@@ -411,7 +431,13 @@ __global__ void __launch_bounds__(NG * 32, 2) pinn_train_kernel(const PinnDesc d
         }
         {
             float *dst = T.partials + (size_t)lb * d.partial_stride;
-            for (int i = threadIdx.x; i < P; i += blockDim.x) dst[i] = g_s[i];
+#pragma unroll
+            for (int l = 0; l <= NH; ++l) {
+                const int nw = d.layers[l] * d.layers[l + 1], nb = d.layers[l + 1];
+                if (l == 0 || l == NH) { for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[woff[l] + i] = g_s[cw[l] + i]; }
+                else { for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[woff[l] + i] = A_s[(l - 1) * WMAX * WMAX + i]; }
+                for (int i = threadIdx.x; i < nb; i += blockDim.x) dst[boff[l] + i] = g_s[cb[l] + i];
+            }
             if (threadIdx.x == 0) { dst[P] = lossR; dst[P + 1] = lossI1; dst[P + 2] = lossI2; dst[P + 3] = lossB; }
         }
       }   // !done
@@ -501,7 +527,9 @@ static KernelPick pick_kernel(const PinnDesc &d)
 
 static size_t smem_bytes(const PinnDesc &d, const KernelPick &k)
 {
-    const int P4 = (d.n_params + 3) & ~3;
+    int PC = 0;                                              // first / last matrix + all biases (the kernel's compact copies)
+    for (int l = 0; l + 1 < d.nlayers; ++l) PC += ((l == 0 || l == d.nlayers - 2) ? d.layers[l] * d.layers[l + 1] : 0) + d.layers[l + 1];
+    const int P4 = (PC + 3) & ~3;
     const int GJ = k.wmax / NG, GJP = (GJ + 3) & ~3;
     const size_t fl = (size_t)2 * P4 + (size_t)2 * (k.nh - 1) * k.wmax * NG * GJP + (size_t)2 * k.wmax * (CH * PT + 1) + (size_t)NG * CH * PT + 8;
     return fl * sizeof(float);

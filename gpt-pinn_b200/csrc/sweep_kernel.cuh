@@ -17,10 +17,14 @@
 //                           gradients through shared memory once per epoch (few items per warp);
 //             PRIV = false: the W warps of a CTA share a 4-deep ring with full/empty mbarriers and
 //                           static rounds (small grids, RL = 32).
-//   T     = per-warp [NQT][RT][4] block, rebuilt from the staged P-derivative tiles for every
-//           residual tile (2 FMA/element amortised over the siblings) so the inner loop spends the
-//           reference's 4n FMA per row and parameter.  PRIV builds it in place over the tile's first
-//           matrix block (the tile copy is the warp's own); the shared ring keeps a block per warp.
+//   T     = per-warp [NQT][RT][4] block so that the inner loop spends the reference's 4n FMA per row and
+//           parameter.  PRIV, wide items: T of every (alpha, beta) group is computed ONCE per launch into
+//           global memory (build_t_kernel: it does not depend on the epoch) and the residual tile arrives
+//           as two bulk copies -- the group's T tile over the slot's first matrix block, [P | vectors]
+//           from the shared stream -- so no warp ever rebuilds it (it used to, for every tile of every
+//           epoch: 8 % of the warp time).  Fallbacks: PRIV builds it in place over the tile's first
+//           matrix block (the tile copy is the warp's own) when the T arrays would not fit the memory
+//           budget; the shared ring keeps a block per warp; narrow items form T rows in registers.
 //   epoch = one pass over the tile stream (all residual, IC, BC tiles); at its end the RL
 //           row-slices are summed with xor-shuffles (fixed order => bitwise deterministic),
 //           the loss of the *current* c falls out of the same pass, then c <- c - lr*grad.
@@ -135,9 +139,21 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
         mbar_arrive_expect_tx(&full[s], SLOT * 4);
         bulk_g2s(ring + s * SLOT, p.packed + (size_t)(lt % tiles_pp) * SLOT, SLOT * 4, &full[s]);
     };
+    int cur_tslot = -1;                      // T array of the item being processed (lane 0 issues the copies)
+    constexpr int PBLK = 2;                  // first block still needed next to a precomputed T (B: P_x, P; KG / AC: P)
+    constexpr uint32_t TBYTES = (uint32_t)TT * 4u, PVBYTES = (uint32_t)(SLOT - PBLK * ARR) * 4u;
     auto issue_priv = [&](uint32_t s) {
-        mbar_arrive_expect_tx(&full[s], SLOT * 4);
-        bulk_g2s(ring + s * SLOT, p.packed + (size_t)next_tile * SLOT, SLOT * 4, &full[s]);
+        if (cur_tslot >= 0 && next_tile < (uint32_t)p.ntile[0]) {
+            // residual tile of a group with a precomputed T: the T tile lands on the slot's first block (streamed once per
+            // epoch, no reuse: evict-first in L2), the blocks the row loop still reads ([P_x] P) and the row vectors come
+            // from the shared stream
+            mbar_arrive_expect_tx(&full[s], TBYTES + PVBYTES);
+            bulk_g2s_stream(ring + s * SLOT, p.tglob + (size_t)cur_tslot * (size_t)p.t_stride + (size_t)next_tile * TT, TBYTES, &full[s]);
+            bulk_g2s(ring + s * SLOT + PBLK * ARR, p.packed + (size_t)next_tile * SLOT + PBLK * ARR, PVBYTES, &full[s]);
+        } else {
+            mbar_arrive_expect_tx(&full[s], SLOT * 4);
+            bulk_g2s(ring + s * SLOT, p.packed + (size_t)next_tile * SLOT, SLOT * 4, &full[s]);
+        }
         next_tile += (uint32_t)K;
         if (next_tile >= tiles_pp) next_tile = (uint32_t)tw;
     };
@@ -198,7 +214,21 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
         const bool active = item < p.n_items;
         ItemDesc it;
         it.tp0 = 0.f; it.tp1 = 0.f; it.sib_start = 0; it.sib_count = 0; it.SL = 32;
+        it.t_slot = -1;
         if (active) it = p.items[item];
+        if (PRIV && p.tglob != nullptr && (it.t_slot >= 0 || cur_tslot >= 0)) {
+            // The NST tiles in flight were issued before this item was known (the ring runs ahead across items), i.e. with the
+            // previous item's T or with none.  Take them out of the ring and issue the first tiles of the pass again, now with
+            // this item's T array: one extra round trip per work item (a work item runs for all epochs).
+            for (int k = 0; k < NST; ++k) { mbar_wait(&full[gt % NST], (gt / NST) & 1); ++gt; }
+            __syncwarp();
+            cur_tslot = it.t_slot;
+            if (lane == 0) {
+                fence_proxy_async();
+                next_tile = (uint32_t)tw;
+                for (uint32_t k = 0; k < (uint32_t)NST; ++k) issue_priv((gt + k) % NST);
+            }
+        }
         const int SL = it.SL, RL = 32 / SL;
         const int sl = lane & (SL - 1), slice = lane / SL;
 
@@ -312,6 +342,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                     // private ring: the staged tile belongs to this warp alone, so T overwrites the first matrix block
                     // (P_tt / P_t: dead once T exists) element by element; shared ring: a block of its own
                     float *Tw = PRIV ? const_cast<float *>(slot) : Tall + warp * TT;
+                    if (!(PRIV && it.t_slot >= 0)) {                // (a precomputed T tile already sits there)
 #pragma unroll
                     for (int e = lane; e < NQT * RT; e += 32) {     // NQT * RT / 32 independent entries: all loads issue before the first use
                         const int q = e / RT, r = e % RT;
@@ -336,6 +367,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
                             set_comp(tv, N % 4, fc);
                         }
                         st4(Tw + o, tv);
+                    }
                     }
                     __syncwarp();
 
