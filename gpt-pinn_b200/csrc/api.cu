@@ -146,6 +146,9 @@ static double per_row_instr(int pde, int n, int M)
     const double fma = (pde == PDE_B ? 6.0 : 4.0) * n;
     return M * (fma + 8.0) + (pde == PDE_B ? 3.0 : 2.0) * ((n + 3) / 4) + 8.0;
 }
+// set by run_sweep before planning: the private-ring kernel will find precomputed T arrays (no T build of any kind there)
+static thread_local bool g_plan_tglob = false;
+
 static double item_instr(int pde, int n, int M, int SL, long long rows_total, long long tiles_pass, int rt, int K = 1, bool shared_ring = false)
 {
     const int RL = 32 / SL;
@@ -157,8 +160,9 @@ static double item_instr(int pde, int n, int M, int SL, long long rows_total, lo
     // wider items build a per-warp T block in shared memory once per tile; plus ring bookkeeping per tile
     // per-tile ring cost in instruction-equivalents (mbarrier wait + first-row load latency, measured on B200)
     const double ring = shared_ring ? 300.0 : 200.0;
-    const double build = SL <= GP_REGT_MAX_SL ? (double)tiles * ring + rows_lane * (2.0 * n + 6.0)
-                                               : (double)tiles * (36.0 * (n / 4 + 1) * rt / 32.0 + ring);
+    const double build = (g_plan_tglob && !shared_ring) ? (double)tiles * ring
+                       : SL <= GP_REGT_MAX_SL ? (double)tiles * ring + rows_lane * (2.0 * n + 6.0)
+                                              : (double)tiles * (36.0 * (n / 4 + 1) * rt / 32.0 + ring);
     (void)rows_total;
     // measured issue efficiency relative to M = 5 (KG n = 15 single-round runs: 0.595 / 0.526 / 0.453 / 0.304 of FP32 peak)
     const double rel = M >= 5 ? 1.0 : (M == 4 ? 0.895 : (M >= 2 ? 0.835 : 0.624));
@@ -574,6 +578,22 @@ static int run_sweep(gptpinn_handle *h, int pde, int n, const Segments &seg, Pac
         if (info) memset(info, 0, sizeof(*info));
         return GPTPINN_OK;
     }
+    // precomputed T arrays (one per (tp0, tp1) group) are used when they fit the memory budget and f_hat is zero; the
+    // planner prices the work items accordingly
+    size_t tglob_budget_mb = 8192;
+    if (const char *ev = getenv("GPTPINN_TGLOB_MB")) tglob_budget_mb = (size_t)std::max(0, atoi(ev));
+    struct FlagGuard { ~FlagGuard() { g_plan_tglob = false; } } flag_guard;       // the flag never outlives this call
+    {
+        std::vector<uint64_t> keys(rows.size());
+        for (size_t i = 0; i < rows.size(); ++i) keys[i] = key_of(rows[i]);
+        std::sort(keys.begin(), keys.end());
+        const size_t ngroups = (size_t)(std::unique(keys.begin(), keys.end()) - keys.begin());
+        const size_t per_group = (size_t)((seg.rows[0] + RT_PRIV - 1) / RT_PRIV) * (size_t)(n / 4 + 1) * 4 * RT_PRIV * sizeof(float);
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const size_t need = ngroups * per_group + ngroups * sizeof(float2) + 256;
+        g_plan_tglob = !has_fhat && !getenv("GPTPINN_NO_TGLOB") && need <= tglob_budget_mb * 1024 * 1024 && need + need / 4 <= h->tglob_cap + free_b / 2;
+    }
     // row-partitioned kernels (sweep_rows.cuh): few parameters, no early-exit bound.  cfg_mode 3 = grid flavour (cooperative
     // launch, any row count), cfg_mode 4 = cluster flavour (cfg_K = CTAs per cluster, 0 = best), cfg_mode 0 = cheapest of
     // the work-item plan and the two flavours by the cost model
@@ -611,6 +631,7 @@ static int run_sweep(gptpinn_handle *h, int pde, int n, const Segments &seg, Pac
         }
         if (a->cfg_mode != 0) {
             if (!best_geo.ok) return fail(GPTPINN_E_UNSUPPORTED, "row-partitioned kernel: needs <= %d parameters per CTA, a cooperative / cluster launch and the row shares in shared memory", ROWS_MAX_PARAMS);
+            g_plan_tglob = false;
             return run_sweep_rows(h, pde, n, seg, jobs, has_fhat, NR, NI, NB, rows, a, info, best_geo, best_G, st);
         }
         if (best_geo.ok) {
@@ -618,12 +639,16 @@ static int run_sweep(gptpinn_handle *h, int pde, int n, const Segments &seg, Pac
             std::vector<ParamRow> tmp(rows);
             int rcp = make_plan(tmp, pde, n, h->n_sm, seg.rows, seg.nseg, a, probe);
             if (rcp) return rcp;
-            if (best_cost < probe.cost)
+            if (best_cost < probe.cost) {
+                g_plan_tglob = false;
                 return run_sweep_rows(h, pde, n, seg, jobs, has_fhat, NR, NI, NB, rows, a, info, best_geo, best_G, st);
+            }
         }
     }
     Plan plan;
     int rc = make_plan(rows, pde, n, h->n_sm, seg.rows, seg.nseg, a, plan);
+    const bool use_tglob = g_plan_tglob;
+    g_plan_tglob = false;
     if (rc) return rc;
 
     const int RT = plan.priv ? RT_PRIV : RT_SHARED;
@@ -660,10 +685,9 @@ static int run_sweep(gptpinn_handle *h, int pde, int n, const Segments &seg, Pac
     //      epoch.  Skipped (in-kernel build) when the arrays exceed the memory budget or f_hat is non-zero.
     std::vector<float2> tgroups;
     const long long tt = (long long)(n / 4 + 1) * 4 * RT, t_stride = (long long)p.ntile[0] * tt;
-    if (plan.priv && !has_fhat && !getenv("GPTPINN_NO_TGLOB")) {
+    if (plan.priv && use_tglob) {
         std::map<uint64_t, int> slot_of;
         for (ItemDesc &it : plan.items) {
-            if (it.SL <= GP_REGT_MAX_SL) continue;
             uint32_t a_, b_;
             memcpy(&a_, &it.tp0, 4); memcpy(&b_, &it.tp1, 4);
             const uint64_t key = ((uint64_t)a_ << 32) | b_;
@@ -671,19 +695,9 @@ static int run_sweep(gptpinn_handle *h, int pde, int n, const Segments &seg, Pac
             if (f == slot_of.end()) { f = slot_of.emplace(key, (int)tgroups.size()).first; tgroups.push_back(make_float2(it.tp0, it.tp1)); }
             it.t_slot = f->second;
         }
-        size_t budget_mb = 8192;
-        if (const char *ev = getenv("GPTPINN_TGLOB_MB")) budget_mb = (size_t)std::max(0, atoi(ev));
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
         const size_t need = (size_t)tgroups.size() * (size_t)t_stride * sizeof(float) + tgroups.size() * sizeof(float2) + 256;
-        const size_t avail = h->tglob_cap + free_b / 2;                          // never take more than half of what is free
-        if (tgroups.empty() || need > budget_mb * 1024 * 1024 || need + need / 4 > avail) {
-            for (ItemDesc &it : plan.items) it.t_slot = -1;
-            tgroups.clear();
-        } else {
-            rc = ensure(&h->tglob, &h->tglob_cap, need);
-            if (rc) return rc;
-        }
+        rc = ensure(&h->tglob, &h->tglob_cap, need);                            // (budget and free memory checked before planning)
+        if (rc) return rc;
     }
 
     if (!h->counter) CUDA_TRY(cudaMalloc((void **)&h->counter, sizeof(unsigned int)));

@@ -265,10 +265,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sweep_kernel(const SweepParams p
             int gbase = 0;                          // pass-relative index of the segment's first tile
             for (int t = (tw - gbase) & (K - 1); t < p.ntile[0]; t += K) {
                 const float *slot = acquire();
-                if (active && (SL <= REGT_MAX_SL || has_fhat)) {
+                if (active && ((SL <= REGT_MAX_SL && !(PRIV && it.t_slot >= 0)) || has_fhat)) {
                     // ---- (also the general path for a non-zero f_hat target -- never the case in the reference's problems --
                     //      which keeps the f_hat handling out of the fast loops below)
-                    // ---- few sibling lanes: a T row is used by at most REGT_MAX_SL lanes, so staging the whole T block
+                    // ---- few sibling lanes and no precomputed T array: a T row is used by at most REGT_MAX_SL lanes, so staging the whole T block
                     //      through shared memory costs more than it saves.  Each lane forms the T quads of its own row in
                     //      registers (fused multiply-adds: within one ulp of the reference's separately rounded T).
                     const float *Pblk = slot + (PDE == PDE_B ? 3 : 2) * ARR;
