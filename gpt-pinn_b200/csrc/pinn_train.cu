@@ -45,23 +45,30 @@ constexpr int NG = 4;                 // neuron groups = warps per block
 constexpr int PT = 32;                // points per tile = lanes
 constexpr int TJG = 4, TIG = 8;       // lane tiling of a weight-gradient matrix: 4 output groups x 8 input groups
 
-__device__ __noinline__ void act_derivs(int act, float z, float &s0, float &s1, float &s2, float &s3)
+// The transcendental part of the activation, evaluated ONCE per (layer, neuron, point) in the forward sweep and kept in a
+// thread-private shared-memory slot for the reverse sweep (the precise sincosf / tanhf with their range reduction were a
+// quarter of the kernel's instructions when every use recomputed them): cos -> (cos z, sin z), tanh -> (tanh z, -).
+__device__ __noinline__ void act_eval(int act, float z, float &p0, float &p1)
+{
+    if (act == 0) { float sn, cs; sincosf(z, &sn, &cs); p0 = cs; p1 = sn; }
+    else { p0 = tanhf(z); p1 = 0.f; }
+}
+// the activation and its first three derivatives from the cached pair
+__device__ __forceinline__ void act_derivs(int act, float p0, float p1, float &s0, float &s1, float &s2, float &s3)
 {
     if (act == 0) {                   // cos
-        float sn, cs;
-        sincosf(z, &sn, &cs);
-        s0 = cs; s1 = -sn; s2 = -cs; s3 = sn;
+        s0 = p0; s1 = -p1; s2 = -p0; s3 = p1;
     } else {                          // tanh
-        const float s = tanhf(z);
+        const float s = p0;
         s0 = s; s1 = 1.f - s * s; s2 = -2.f * s * s1; s3 = s1 * (6.f * s * s - 2.f);
     }
 }
 
 // five channels of a = sigma(z) from the five channels of z
-__device__ __forceinline__ void act_forward(int act, const float (&z)[CH], float (&a)[CH])
+__device__ __forceinline__ void act_forward(int act, float p0, float p1, const float (&z)[CH], float (&a)[CH])
 {
     float s0, s1, s2, s3;
-    act_derivs(act, z[0], s0, s1, s2, s3);
+    act_derivs(act, p0, p1, s0, s1, s2, s3);
     a[0] = s0;
     a[1] = s1 * z[1];
     a[2] = s1 * z[2];
@@ -70,10 +77,10 @@ __device__ __forceinline__ void act_forward(int act, const float (&z)[CH], float
 }
 
 // adjoint of the five channels of z given the adjoint of the five channels of a = sigma(z)
-__device__ __forceinline__ void act_backward(int act, const float (&z)[CH], const float (&ab)[CH], float (&zb)[CH])
+__device__ __forceinline__ void act_backward(int act, float p0, float p1, const float (&z)[CH], const float (&ab)[CH], float (&zb)[CH])
 {
     float s0, s1, s2, s3;
-    act_derivs(act, z[0], s0, s1, s2, s3);
+    act_derivs(act, p0, p1, s0, s1, s2, s3);
     const float zx = z[1], zt = z[2];
     zb[3] = s1 * ab[3];
     zb[4] = s1 * ab[4];
@@ -116,6 +123,8 @@ __global__ void __launch_bounds__(NG * 32, GP_PINN_MINB) pinn_train_kernel(const
     float *A_s = wp_s + (NH - 1) * WMAX * NG * GJP;          // [WMAX][CH][PT]
     float *B_s = A_s + STG;                                  // [WMAX][CH][PT]
     float *U_s = B_s + STG;                                  // [NG][CH][PT] partial network outputs
+    float *S_s = U_s + NG * CH * PT + 8;                     // [NH][GJ][2][threads] cached (cos, sin) / (tanh, -): every slot is read back by the thread that wrote it
+    auto sslot = [&](int l, int jj, int comp) -> float & { return S_s[((l * GJ + jj) * 2 + comp) * (NG * 32) + threadIdx.x]; };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int j0 = warp * GJ;                                // first neuron owned by this thread in every hidden layer
     const int tjg = lane / TIG, tig = lane % TIG;
@@ -197,7 +206,10 @@ __global__ void __launch_bounds__(NG * 32, GP_PINN_MINB) pinn_train_kernel(const
                     float zz[CH], aa[CH];
 #pragma unroll
                     for (int c = 0; c < CH; ++c) zz[c] = z[l][c][jj];
-                    act_forward(d.act, zz, aa);
+                    float p0, p1;
+                    act_eval(d.act, zz[0], p0, p1);
+                    sslot(l, jj, 0) = p0; sslot(l, jj, 1) = p1;
+                    act_forward(d.act, p0, p1, zz, aa);
                     const bool ok = (j0 + jj) < d.layers[l + 1];
 #pragma unroll
                     for (int c = 0; c < CH; ++c) A_s[(j0 + jj) * NS + c * PT + lane] = ok ? aa[c] : 0.f;
@@ -317,7 +329,7 @@ __global__ void __launch_bounds__(NG * 32, GP_PINN_MINB) pinn_train_kernel(const
                     float zz[CH], aa[CH], zb[CH];
 #pragma unroll
                     for (int c = 0; c < CH; ++c) { zz[c] = z[l][c][jj]; aa[c] = ab[c][jj]; }
-                    act_backward(d.act, zz, aa, zb);
+                    act_backward(d.act, sslot(l, jj, 0), sslot(l, jj, 1), zz, aa, zb);
 #pragma unroll
                     for (int c = 0; c < CH; ++c) ab[c][jj] = zb[c];
                 }
@@ -349,7 +361,7 @@ __global__ void __launch_bounds__(NG * 32, GP_PINN_MINB) pinn_train_kernel(const
                         float zz[CH], aa[CH];
 #pragma unroll
                         for (int c = 0; c < CH; ++c) zz[c] = z[l - 1][c][jj];
-                        act_forward(d.act, zz, aa);
+                        act_forward(d.act, sslot(l > 0 ? l - 1 : 0, jj, 0), sslot(l > 0 ? l - 1 : 0, jj, 1), zz, aa);
                         const bool okA = (j0 + jj) < d.layers[l], okB = (j0 + jj) < d.layers[l + 1];
 #pragma unroll
                         for (int c = 0; c < CH; ++c) {
@@ -532,7 +544,8 @@ static size_t smem_bytes(const PinnDesc &d, const KernelPick &k)
     for (int l = 0; l + 1 < d.nlayers; ++l) PC += ((l == 0 || l == d.nlayers - 2) ? d.layers[l] * d.layers[l + 1] : 0) + d.layers[l + 1];
     const int P4 = (PC + 3) & ~3;
     const int GJ = k.wmax / NG, GJP = (GJ + 3) & ~3;
-    const size_t fl = (size_t)2 * P4 + (size_t)2 * (k.nh - 1) * k.wmax * NG * GJP + (size_t)2 * k.wmax * (CH * PT + 1) + (size_t)NG * CH * PT + 8;
+    const size_t fl = (size_t)2 * P4 + (size_t)2 * (k.nh - 1) * k.wmax * NG * GJP + (size_t)2 * k.wmax * (CH * PT + 1) + (size_t)NG * CH * PT + 8
+                      + (size_t)k.nh * GJ * 2 * NG * 32;                          // cached activation pairs
     return fl * sizeof(float);
 }
 
