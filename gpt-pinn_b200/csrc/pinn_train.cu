@@ -48,7 +48,7 @@ constexpr int TJG = 4, TIG = 8;       // lane tiling of a weight-gradient matrix
 // The transcendental part of the activation, evaluated ONCE per (layer, neuron, point) in the forward sweep and kept in a
 // thread-private shared-memory slot for the reverse sweep (the precise sincosf / tanhf with their range reduction were a
 // quarter of the kernel's instructions when every use recomputed them): cos -> (cos z, sin z), tanh -> (tanh z, -).
-__device__ __noinline__ void act_eval(int act, float z, float &p0, float &p1)
+__device__ __forceinline__ void act_eval(int act, float z, float &p0, float &p1)
 {
     if (act == 0) { float sn, cs; sincosf(z, &sn, &cs); p0 = cs; p1 = sn; }
     else { p0 = tanhf(z); p1 = 0.f; }
