@@ -617,7 +617,12 @@ static int run_sweep(gptpinn_handle *h, int pde, int n, const Segments &seg, Pac
                 if ((a->Np + C - 1) / C > ROWS_MAX_PARAMS) continue;
                 RowsGeom geo = rows_geometry(pde, n, (a->Np + C - 1) / C, seg, S, 0, S, C);
                 if (!geo.ok) continue;
-                const int fit = kRowsClusters[pde][n - 1](S, geo.smem);                  // co-resident clusters of this shape
+                // co-resident clusters of this shape (driver query: cached per (device, pde, n, S, shared-memory size))
+                static thread_local std::map<std::pair<long long, size_t>, int> fit_cache;
+                const std::pair<long long, size_t> fkey(((long long)dev << 32) | (pde << 16) | (n << 8) | S, geo.smem);
+                auto fc = fit_cache.find(fkey);
+                if (fc == fit_cache.end()) fc = fit_cache.emplace(fkey, kRowsClusters[pde][n - 1](S, geo.smem)).first;
+                const int fit = fc->second;
                 if (fit < 1) continue;
                 if (fit < C) {
                     C = fit;
