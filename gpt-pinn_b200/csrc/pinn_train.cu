@@ -48,7 +48,15 @@ constexpr int TJG = 4, TIG = 8;       // lane tiling of a weight-gradient matrix
 // The transcendental part of the activation, evaluated ONCE per (layer, neuron, point) in the forward sweep and kept in a
 // thread-private shared-memory slot for the reverse sweep (the precise sincosf / tanhf with their range reduction were a
 // quarter of the kernel's instructions when every use recomputed them): cos -> (cos z, sin z), tanh -> (tanh z, -).
-__device__ __forceinline__ void act_eval(int act, float z, float &p0, float &p1)
+#ifndef GP_PINN_ACT_INLINE
+#define GP_PINN_ACT_INLINE 1          // 0: the precise sincosf / tanhf live in ONE out-of-line copy instead of 20 inlined ones
+#endif
+#if GP_PINN_ACT_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+void act_eval(int act, float z, float &p0, float &p1)
 {
     if (act == 0) { float sn, cs; sincosf(z, &sn, &cs); p0 = cs; p1 = sn; }
     else { p0 = tanhf(z); p1 = 0.f; }
@@ -91,7 +99,9 @@ __device__ __forceinline__ void act_backward(int act, float p0, float p1, const 
 }
 
 // WMAX: widest hidden layer (all hidden layers are padded to it), NH: hidden layers (KG 2, Burgers 4)
-template <int WMAX, int NH>
+// ACT: the activation (0 cos, 1 tanh) as a compile-time constant -- with a run-time switch every one of the 20 activation
+// sites of a tile carried both sincosf and tanhf, a third of the kernel's 140 KB of code (more than the instruction cache)
+template <int WMAX, int NH, int ACT>
 __global__ void __launch_bounds__(NG * 32, GP_PINN_MINB) pinn_train_kernel(const PinnDesc d, const PinnBatch bt)
 {
     // this CTA's training: group `tr` of the grid, local CTA index `lb`; CTAs beyond n * group only keep the barriers
@@ -207,9 +217,9 @@ __global__ void __launch_bounds__(NG * 32, GP_PINN_MINB) pinn_train_kernel(const
 #pragma unroll
                     for (int c = 0; c < CH; ++c) zz[c] = z[l][c][jj];
                     float p0, p1;
-                    act_eval(d.act, zz[0], p0, p1);
+                    act_eval(ACT, zz[0], p0, p1);
                     sslot(l, jj, 0) = p0; sslot(l, jj, 1) = p1;
-                    act_forward(d.act, p0, p1, zz, aa);
+                    act_forward(ACT, p0, p1, zz, aa);
                     const bool ok = (j0 + jj) < d.layers[l + 1];
 #pragma unroll
                     for (int c = 0; c < CH; ++c) A_s[(j0 + jj) * NS + c * PT + lane] = ok ? aa[c] : 0.f;
@@ -329,7 +339,7 @@ __global__ void __launch_bounds__(NG * 32, GP_PINN_MINB) pinn_train_kernel(const
                     float zz[CH], aa[CH], zb[CH];
 #pragma unroll
                     for (int c = 0; c < CH; ++c) { zz[c] = z[l][c][jj]; aa[c] = ab[c][jj]; }
-                    act_backward(d.act, sslot(l, jj, 0), sslot(l, jj, 1), zz, aa, zb);
+                    act_backward(ACT, sslot(l, jj, 0), sslot(l, jj, 1), zz, aa, zb);
 #pragma unroll
                     for (int c = 0; c < CH; ++c) ab[c][jj] = zb[c];
                 }
@@ -361,7 +371,7 @@ __global__ void __launch_bounds__(NG * 32, GP_PINN_MINB) pinn_train_kernel(const
                         float zz[CH], aa[CH];
 #pragma unroll
                         for (int c = 0; c < CH; ++c) zz[c] = z[l - 1][c][jj];
-                        act_forward(d.act, sslot(l > 0 ? l - 1 : 0, jj, 0), sslot(l > 0 ? l - 1 : 0, jj, 1), zz, aa);
+                        act_forward(ACT, sslot(l > 0 ? l - 1 : 0, jj, 0), sslot(l > 0 ? l - 1 : 0, jj, 1), zz, aa);
                         const bool okA = (j0 + jj) < d.layers[l], okB = (j0 + jj) < d.layers[l + 1];
 #pragma unroll
                         for (int c = 0; c < CH; ++c) {
@@ -520,22 +530,28 @@ __global__ void __launch_bounds__(NG * 32, GP_PINN_MINB) pinn_train_kernel(const
 
 struct KernelPick { void *fn; int wmax, nh; };
 
+template <int ACT>
+static KernelPick pick_kernel_act(int maxw, int nh)
+{
+    if (maxw <= 20) {
+        if (nh == 1) return {(void *)pinn_train_kernel<20, 1, ACT>, 20, 1};
+        if (nh == 2) return {(void *)pinn_train_kernel<20, 2, ACT>, 20, 2};
+        if (nh == 3) return {(void *)pinn_train_kernel<20, 3, ACT>, 20, 3};
+        if (nh == 4) return {(void *)pinn_train_kernel<20, 4, ACT>, 20, 4};
+    } else if (maxw <= 40) {
+        if (nh == 1) return {(void *)pinn_train_kernel<40, 1, ACT>, 40, 1};
+        if (nh == 2) return {(void *)pinn_train_kernel<40, 2, ACT>, 40, 2};
+        if (nh == 3) return {(void *)pinn_train_kernel<40, 3, ACT>, 40, 3};
+    }
+    return {nullptr, 0, 0};
+}
+
 static KernelPick pick_kernel(const PinnDesc &d)
 {
     const int nh = d.nlayers - 2;
     int maxw = 0;
     for (int l = 1; l < d.nlayers - 1; ++l) maxw = d.layers[l] > maxw ? d.layers[l] : maxw;
-    if (maxw <= 20) {
-        if (nh == 1) return {(void *)pinn_train_kernel<20, 1>, 20, 1};
-        if (nh == 2) return {(void *)pinn_train_kernel<20, 2>, 20, 2};
-        if (nh == 3) return {(void *)pinn_train_kernel<20, 3>, 20, 3};
-        if (nh == 4) return {(void *)pinn_train_kernel<20, 4>, 20, 4};
-    } else if (maxw <= 40) {
-        if (nh == 1) return {(void *)pinn_train_kernel<40, 1>, 40, 1};
-        if (nh == 2) return {(void *)pinn_train_kernel<40, 2>, 40, 2};
-        if (nh == 3) return {(void *)pinn_train_kernel<40, 3>, 40, 3};
-    }
-    return {nullptr, 0, 0};
+    return d.act == 0 ? pick_kernel_act<0>(maxw, nh) : pick_kernel_act<1>(maxw, nh);
 }
 
 static size_t smem_bytes(const PinnDesc &d, const KernelPick &k)

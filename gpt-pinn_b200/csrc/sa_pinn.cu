@@ -12,8 +12,13 @@
 // All points (collocation, initial, lower / upper boundary) run as ONE batch of N points; tensors are [4][N][W]
 // (channel-major, W = hidden width), so every hidden->hidden map of all four channels is one [4N x W] x [W x W] GEMM
 // -- a plain library GEMM (cuBLAS through torch.mm on the host side, gptpinn/sa_pinn.py); everything else is here.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include <type_traits>
 
 #include "../../include/gptpinn_b200.h"
 
@@ -181,6 +186,188 @@ static inline unsigned blocks_for(long long n, int threads)
     return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+
+// ---- L-BFGS direction (eager_lbfgs.py:80-106: the two-loop recursion) in ONE launch ------------------------------------------
+// d = -H g with H from the k most recent (s, y) pairs: q = -g; for i = k-1..0: al_i = ro_i <s_i, q>, q -= al_i y_i;
+// r = Hdiag q; for i = 0..k-1: be_i = ro_i <y_i, r>, r += (al_i - be_i) s_i.  2k dependent (dot, axpy) steps over a vector
+// of P ~ 5*10^4 weights: as 4k tiny library launches it was the bulk of an L-BFGS iteration.  One CTA, the vector lives
+// in shared memory (every thread owns the same elements in every pass, so the passes need no barrier of their own), the
+// history rows stream from L2.  The update of step i is merged with the dot product of step i +- 1 (2k + 1 passes, two
+// rows in flight per pass); block sums in a fixed order (deterministic); the separately rounded multiply and subtract / add
+// of the tensor expressions are kept.  The pairs sit in a ring of `hist` rows, pair i (oldest first) in row (start + i) % hist.
+constexpr int LB_THREADS = 1024;
+
+__device__ __forceinline__ float lb_block_sum(float v, float *red, float *bc)
+{
+    for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float s = threadIdx.x < (LB_THREADS >> 5) ? red[threadIdx.x] : 0.f;
+        for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (threadIdx.x == 0) *bc = s;
+    }
+    __syncthreads();
+    return *bc;                                  // (the next call rewrites *bc only after its first barrier)
+}
+
+// one pass over the thread's own elements: q <- upd(q, U) (if U), then the partial sum of q . D (if D)
+//   MODE 0: q = q - a U        MODE 1: q = (q - a U) * h        MODE 2: q = q + a U
+template <int MODE, typename V, int THREADS = LB_THREADS>
+__device__ __forceinline__ float lb_pass(V *q, const V *U, float a, float h, const V *D, int n)
+{
+    constexpr int L = sizeof(V) / sizeof(float);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    auto one = [&](int e, int slot) {
+        V qv = q[e];
+        float *qf = reinterpret_cast<float *>(&qv);
+        if (U) {
+            const V uv = U[e];
+            const float *uf = reinterpret_cast<const float *>(&uv);
+#pragma unroll
+            for (int c = 0; c < L; ++c) {
+                if (MODE == 2) qf[c] = __fadd_rn(qf[c], __fmul_rn(a, uf[c]));
+                else qf[c] = __fsub_rn(qf[c], __fmul_rn(a, uf[c]));
+                if (MODE == 1) qf[c] = __fmul_rn(qf[c], h);
+            }
+            q[e] = qv;
+        } else if (MODE == 1) {
+#pragma unroll
+            for (int c = 0; c < L; ++c) qf[c] = __fmul_rn(qf[c], h);
+            q[e] = qv;
+        }
+        if (D) {
+            const V dv = D[e];
+            const float *df = reinterpret_cast<const float *>(&dv);
+#pragma unroll
+            for (int c = 0; c < L; ++c) acc[slot] = fmaf(df[c], qf[c], acc[slot]);
+        }
+    };
+    int e = threadIdx.x;
+    for (; e + 3 * THREADS < n; e += 4 * THREADS) {
+        one(e, 0); one(e + THREADS, 1); one(e + 2 * THREADS, 2); one(e + 3 * THREADS, 3);
+    }
+    for (; e < n; e += THREADS) one(e, 0);
+    return (acc[0] + acc[1]) + (acc[2] + acc[3]);
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(LB_THREADS, 1)
+sa_lbfgs_direction_kernel(const float *__restrict__ S, const float *__restrict__ Y, const float *__restrict__ ro, int k, int start,
+                          int hist, long long ld, int P, float Hdiag, const float *__restrict__ g, float *__restrict__ d)
+{
+    extern __shared__ __align__(16) float q[];   // [P]
+    __shared__ float red[32], al[256], bc;
+    const int tid = threadIdx.x;
+    const int nv = VEC ? P / 4 : 0;              // float4 part (rows, g and d 16-byte aligned), then the scalar tail
+    const int t0 = 4 * nv, nt = P - t0;
+    auto row = [&](const float *base, int i) { return base + (long long)((start + i) % hist) * ld; };
+    // both parts of a pass; the tail elements belong to the first threads
+    auto pass = [&](auto mode, const float *U, float a, float h, const float *D) -> float {
+        constexpr int MODE = decltype(mode)::value;
+        float s = 0.f;
+        if (VEC) s = lb_pass<MODE, float4>(reinterpret_cast<float4 *>(q), reinterpret_cast<const float4 *>(U), a, h,
+                                           reinterpret_cast<const float4 *>(D), nv);
+        s += lb_pass<MODE, float>(q + t0, U ? U + t0 : nullptr, a, h, D ? D + t0 : nullptr, nt);
+        return s;
+    };
+    using M0 = std::integral_constant<int, 0>; using M1 = std::integral_constant<int, 1>; using M2 = std::integral_constant<int, 2>;
+
+    for (int e = tid; e < nv; e += LB_THREADS) {
+        const float4 v = reinterpret_cast<const float4 *>(g)[e];
+        reinterpret_cast<float4 *>(q)[e] = make_float4(-v.x, -v.y, -v.z, -v.w);
+    }
+    for (int e = tid; e < nt; e += LB_THREADS) q[t0 + e] = -g[t0 + e];
+    // first loop, newest pair first: the update with pair i + 1 rides in the pass that forms <s_i, q>
+    float a = 0.f;
+    for (int i = k - 1; i >= 0; --i) {
+        const float part = pass(M0(), i + 1 < k ? row(Y, i + 1) : nullptr, a, 0.f, row(S, i));
+        a = __fmul_rn(lb_block_sum(part, red, &bc), ro[(start + i) % hist]);
+        if (tid == 0) al[i] = a;
+    }
+    // q -= al_0 y_0, r = Hdiag q, and <y_0, r> in one pass
+    float part = pass(M1(), k > 0 ? row(Y, 0) : nullptr, a, Hdiag, k > 0 ? row(Y, 0) : nullptr);
+    __syncthreads();                             // al[] visible (k == 1 has no barrier between the write and the read)
+    for (int i = 0; i < k; ++i) {
+        const float be = __fmul_rn(lb_block_sum(part, red, &bc), ro[(start + i) % hist]);
+        const float coef = __fsub_rn(al[i], be);
+        part = pass(M2(), row(S, i), coef, 0.f, i + 1 < k ? row(Y, i + 1) : nullptr);
+    }
+    for (int e = tid; e < nv; e += LB_THREADS) reinterpret_cast<float4 *>(d)[e] = reinterpret_cast<const float4 *>(q)[e];
+    for (int e = tid; e < nt; e += LB_THREADS) d[t0 + e] = q[t0 + e];
+}
+
+
+// The same recursion on a thread-block CLUSTER: the vector is cut into LBC_CTAS slices, one per CTA (each slice in its CTA's
+// shared memory, each CTA streams only its slice of the history rows: LBC_CTAS times the L2 bandwidth and loads in flight of
+// one SM).  A dot product = block sums -> every CTA's sum written into every CTA's exchange slot through distributed shared
+// memory -> one cluster barrier -> every thread adds the LBC_CTAS sums in rank order (same bits on every CTA).  Slots alternate
+// with the pass parity: a CTA one barrier ahead writes the other slot.  16-byte aligned rows only (the caller falls back).
+constexpr int LBC_CTAS = 8, LBC_THREADS = 512;
+
+__global__ void __launch_bounds__(LBC_THREADS, 1)
+sa_lbfgs_direction_cluster_kernel(const float *__restrict__ S, const float *__restrict__ Y, const float *__restrict__ ro, int k, int start,
+                                  int hist, long long ld, int P, float Hdiag, const float *__restrict__ g, float *__restrict__ d)
+{
+    namespace cgx = cooperative_groups;
+    cgx::cluster_group cluster = cgx::this_cluster();
+    extern __shared__ __align__(16) float q[];   // this CTA's slice
+    __shared__ float red[32], al[256], xch[2][LBC_CTAS];
+    const int tid = threadIdx.x, rank = (int)cluster.block_rank();
+    const int nv = P / 4, per = (nv + LBC_CTAS - 1) / LBC_CTAS;                  // float4s per slice
+    const int v0 = min(rank * per, nv), v1 = min(v0 + per, nv), n4 = v1 - v0;
+    const int lo = 4 * v0, t0 = 4 * nv;
+    const int nt = rank == LBC_CTAS - 1 ? P - t0 : 0;                            // the last CTA also owns the scalar tail
+    float *qt = q + 4 * n4;                                                      // (tail elements sit behind the float4 part)
+    auto row = [&](const float *base, int i) { return base + (long long)((start + i) % hist) * ld; };
+    int parity = 0;
+    auto pass = [&](auto mode, const float *U, float a, float h, const float *D) -> float {
+        constexpr int MODE = decltype(mode)::value;
+        float s = lb_pass<MODE, float4, LBC_THREADS>(reinterpret_cast<float4 *>(q), U ? reinterpret_cast<const float4 *>(U + lo) : nullptr, a, h,
+                                                     D ? reinterpret_cast<const float4 *>(D + lo) : nullptr, n4);
+        if (nt > 0) s += lb_pass<MODE, float, LBC_THREADS>(qt, U ? U + t0 : nullptr, a, h, D ? D + t0 : nullptr, nt);
+        return s;
+    };
+    auto cluster_sum = [&](float v) -> float {
+        for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if ((tid & 31) == 0) red[tid >> 5] = v;
+        __syncthreads();
+        if (tid < 32) {
+            float s = tid < (LBC_THREADS >> 5) ? red[tid] : 0.f;
+            for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (tid < LBC_CTAS) cluster.map_shared_rank(&xch[0][0], tid)[parity * LBC_CTAS + rank] = s;
+        }
+        cluster.sync();
+        float tot = 0.f;
+#pragma unroll
+        for (int r = 0; r < LBC_CTAS; ++r) tot += xch[parity][r];
+        parity ^= 1;
+        return tot;
+    };
+    using M0 = std::integral_constant<int, 0>; using M1 = std::integral_constant<int, 1>; using M2 = std::integral_constant<int, 2>;
+
+    for (int e = tid; e < n4; e += LBC_THREADS) {
+        const float4 v = reinterpret_cast<const float4 *>(g + lo)[e];
+        reinterpret_cast<float4 *>(q)[e] = make_float4(-v.x, -v.y, -v.z, -v.w);
+    }
+    for (int e = tid; e < nt; e += LBC_THREADS) qt[e] = -g[t0 + e];
+    float a = 0.f;
+    for (int i = k - 1; i >= 0; --i) {
+        const float part = pass(M0(), i + 1 < k ? row(Y, i + 1) : nullptr, a, 0.f, row(S, i));
+        a = __fmul_rn(cluster_sum(part), ro[(start + i) % hist]);
+        if (tid == 0) al[i] = a;
+    }
+    float part = pass(M1(), k > 0 ? row(Y, 0) : nullptr, a, Hdiag, k > 0 ? row(Y, 0) : nullptr);
+    __syncthreads();
+    for (int i = 0; i < k; ++i) {
+        const float be = __fmul_rn(cluster_sum(part), ro[(start + i) % hist]);
+        const float coef = __fsub_rn(al[i], be);
+        part = pass(M2(), row(S, i), coef, 0.f, i + 1 < k ? row(Y, i + 1) : nullptr);
+    }
+    for (int e = tid; e < n4; e += LBC_THREADS) reinterpret_cast<float4 *>(d + lo)[e] = reinterpret_cast<const float4 *>(q)[e];
+    for (int e = tid; e < nt; e += LBC_THREADS) d[t0 + e] = qt[e];
+}
+
 }  // namespace gp
 
 using namespace gp;
@@ -259,6 +446,42 @@ extern "C" int gptpinn_sa_adam(float *p_dev, float *m_dev, float *v_dev, const f
     SA_CHECK(p_dev && m_dev && v_dev && g_dev && step_dev && n > 0, "gptpinn_sa_adam");
     sa_adam_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p_dev, m_dev, v_dev, g_dev, n, step_dev, lr, beta1, beta2,
                                                                        (float)eps, ascent ? -1.f : 1.f);
+    SA_LAUNCHED();
+    return GPTPINN_OK;
+}
+
+extern "C" int gptpinn_sa_lbfgs_max_params(void) { return (int)((220 * 1024) / sizeof(float)); }
+
+extern "C" int gptpinn_sa_lbfgs_direction(const float *S_dev, const float *Y_dev, const float *ro_dev, int k, int start, int hist,
+                                          long long ld, long long P, double Hdiag, const float *g_dev, float *d_dev, void *stream)
+{
+    SA_CHECK(g_dev && d_dev && P > 0 && k >= 0 && k <= 256 && (k == 0 || (S_dev && Y_dev && ro_dev && ld >= P && hist >= k && start >= 0 && start < hist)),
+             "gptpinn_sa_lbfgs_direction");
+    SA_CHECK(P <= gptpinn_sa_lbfgs_max_params(), "gptpinn_sa_lbfgs_direction: vector too long for one CTA's shared memory");
+    const size_t smem = (size_t)P * sizeof(float);
+    auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    const bool vec = al16(g_dev) && al16(d_dev) && (k == 0 || (al16(S_dev) && al16(Y_dev) && ld % 4 == 0));
+    static const bool no_cluster = getenv("GPTPINN_LBFGS_NO_CLUSTER") != nullptr;      // experiments: the one-CTA kernel for every size
+    if (vec && k > 0 && P >= 8192 && !no_cluster) {
+        // thread-block cluster of LBC_CTAS CTAs, one slice of the vector each
+        const int per = ((int)(P / 4) + gp::LBC_CTAS - 1) / gp::LBC_CTAS;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(gp::LBC_CTAS); cfg.blockDim = dim3(gp::LBC_THREADS);
+        cfg.dynamicSmemBytes = (size_t)(4 * per + 4) * sizeof(float);
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = gp::LBC_CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, gp::sa_lbfgs_direction_cluster_kernel, S_dev, Y_dev, ro_dev, k, start, hist, ld, (int)P, (float)Hdiag,
+                               g_dev, d_dev) == cudaSuccess)
+            return GPTPINN_OK;
+        (void)cudaGetLastError();                                                      // cluster launch refused: one CTA does it
+    }
+    auto kern = vec ? gp::sa_lbfgs_direction_kernel<true> : gp::sa_lbfgs_direction_kernel<false>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return GPTPINN_E_CUDA;
+    kern<<<1, gp::LB_THREADS, smem, (cudaStream_t)stream>>>(S_dev, Y_dev, ro_dev, k, k > 0 ? start : 0, k > 0 ? hist : 1, ld, (int)P, (float)Hdiag,
+                                                           g_dev, d_dev);
     SA_LAUNCHED();
     return GPTPINN_OK;
 }

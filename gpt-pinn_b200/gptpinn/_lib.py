@@ -78,7 +78,8 @@ EXPORTS = ("gptpinn_version", "gptpinn_last_error", "gptpinn_create", "gptpinn_d
            "gptpinn_mlp_channels", "gptpinn_ffma_peak", "gptpinn_kg_plan", "gptpinn_pinn_train",
            "gptpinn_pinn_train_batch",
            "gptpinn_sa_layer0", "gptpinn_sa_act_forward", "gptpinn_sa_act_backward", "gptpinn_sa_output_forward",
-           "gptpinn_sa_loss_workspace_floats", "gptpinn_sa_loss", "gptpinn_sa_output_backward", "gptpinn_sa_tick", "gptpinn_sa_adam")
+           "gptpinn_sa_loss_workspace_floats", "gptpinn_sa_loss", "gptpinn_sa_output_backward", "gptpinn_sa_tick", "gptpinn_sa_adam",
+           "gptpinn_sa_lbfgs_max_params", "gptpinn_sa_lbfgs_direction")
 
 _lib = None
 

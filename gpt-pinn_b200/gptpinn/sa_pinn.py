@@ -72,6 +72,16 @@ class CudaOps:
     def tick(self, step):
         _lib.check(self.L.gptpinn_sa_tick(self._p(step), self._s()), "gptpinn_sa_tick")
 
+    def lbfgs_capacity(self):
+        return int(self.L.gptpinn_sa_lbfgs_max_params())
+
+    def lbfgs_direction(self, S, Y, ro, k, start, Hdiag, g, d):
+        """d = -H g from the k most recent (s, y) pairs (ring rows start, start + 1, ... mod S.shape[0]): the whole two-loop
+        recursion in one launch"""
+        _lib.check(self.L.gptpinn_sa_lbfgs_direction(self._p(S), self._p(Y), self._p(ro), C.c_int(k), C.c_int(start), C.c_int(S.shape[0]),
+                                                     C.c_longlong(S.stride(0)), C.c_longlong(g.numel()), C.c_double(Hdiag), self._p(g),
+                                                     self._p(d), self._s()), "gptpinn_sa_lbfgs_direction")
+
     def adam(self, p, m, v, g, step, lr, beta1, beta2, eps, sign):
         _lib.check(self.L.gptpinn_sa_adam(self._p(p), self._p(m), self._p(v), self._p(g), C.c_longlong(p.numel()), self._p(step),
                                           C.c_double(lr), C.c_double(beta1), C.c_double(beta2), C.c_double(eps), C.c_int(1 if sign < 0 else 0),
@@ -221,15 +231,27 @@ class SAPinn:
         return rec
 
     # ------------------------------------------------------------------ L-BFGS phase (eager_lbfgs.py:14-200)
-    def lbfgs_fit(self, max_iter, learning_rate=0.8, history=50, record=False, verbose=False):
-        """Fixed-step L-BFGS on the network weights (w_f, w_u frozen), literal two-loop recursion with the reference's
-        stopping tests.  Returns the list of losses (f_hist) when record."""
-        tolFun, tolX = 1e-5, 1e-9
+    def lbfgs_fit(self, max_iter, learning_rate=0.8, history=50, record=False, verbose=False, use_fused=True, tolFun=1e-5, tolX=1e-9):
+        """Fixed-step L-BFGS on the network weights (w_f, w_u frozen): the two-loop recursion and the stopping tests of
+        eager_lbfgs.py:14-200, statement for statement in their effect, arranged so that an iteration reads the device ONCE:
+
+          * the (s, y) pairs live in a ring of `history` rows (no shifting), and the direction d = -H g comes from one kernel
+            launch (gptpinn_sa_lbfgs_direction) instead of 4k small tensor operations;
+          * the step x += t d is taken and the loss / gradient at the new point evaluated BEFORE the host sees gtd = <g, d>;
+            the six scalars an iteration decides on (gtd, sum|d|, f, sum|g|, <y, s>, <y, y>) come back in one transfer.  Should
+            gtd fail the reference's progress test (gtd > -tolX: break before the step) the saved x is put back and the state
+            re-evaluated there, which is what the reference's loop leaves behind.
+
+        Returns the list of losses (f_hist)."""
+        dt, dev, P = self.dtype, self.dev, self.P
+        fused = (use_fused and hasattr(self.ops, "lbfgs_direction") and dt == torch.float32 and history <= 256
+                 and P <= self.ops.lbfgs_capacity())
         x = self.theta
-        S = torch.zeros(history, self.P, dtype=self.dtype, device=self.dev)       # old_dirs
-        Y = torch.zeros(history, self.P, dtype=self.dtype, device=self.dev)       # old_stps
-        ro = torch.zeros(history, dtype=self.dtype, device=self.dev)
-        k = 0
+        ld = (P + 3) & ~3                                                          # 16-byte aligned rows for the kernel's float4 path
+        S = torch.zeros(history, ld, dtype=dt, device=dev)[:, :P]                  # old_dirs  (ring)
+        Y = torch.zeros(history, ld, dtype=dt, device=dev)[:, :P]                  # old_stps  (ring)
+        ro = torch.zeros(history, dtype=dt, device=dev)
+        k, head = 0, 0                                                             # pairs held; ring row of the oldest
         Hdiag = 1.0
         f_hist = []
         if max_iter <= 0:
@@ -241,51 +263,61 @@ class SAPinn:
         evals = 1
         if gsum <= tolFun:
             return f_hist
-        d = t = g_old = None
+        x_prev = torch.empty_like(x)
+        s_buf = y_buf = None                                                       # s = d t, y = g - g_old of the step just taken
+        ys = yy = 0.0
         n_iter = 0
         while n_iter < max_iter:
             n_iter += 1
             if n_iter == 1:
                 d = -g
-            else:
-                y = g - g_old
-                s = d * t
-                ys, yy = torch.stack((torch.dot(y, s), torch.dot(y, y))).tolist()          # host sync 1 of 2
-                if ys > 1e-10:
-                    if k == history:                      # shift the history by one (limited memory)
-                        S = torch.roll(S, -1, 0); Y = torch.roll(Y, -1, 0); ro = torch.roll(ro, -1, 0)
-                        k -= 1
-                    S[k].copy_(s); Y[k].copy_(y)
-                    ro[k] = 1.0 / ys
-                    k += 1
-                    Hdiag = ys / yy
-                # two-loop recursion entirely on the device (the scalars al_i, be_i stay 0-dim tensors)
-                al = [None] * k
-                q = -g
-                for i in range(k - 1, -1, -1):
-                    al[i] = torch.dot(S[i], q) * ro[i]
-                    q = q - al[i] * Y[i]
-                r = q * Hdiag
-                for i in range(k):
-                    be_i = torch.dot(Y[i], r) * ro[i]
-                    r = r + (al[i] - be_i) * S[i]
-                d = r
-            g_old = g
-            gtd = torch.dot(g, d)
-            dsum = d.abs().sum()
-            if n_iter == 1:
-                gtd_h, dsum_h = torch.stack((gtd, dsum)).tolist()
                 t = min(1.0, 1.0 / gsum)
             else:
-                gtd_h, dsum_h = torch.stack((gtd, dsum)).tolist()                         # host sync 2 of 2
+                if ys > 1e-10:
+                    if k == history:                      # limited memory: the newest pair replaces the oldest
+                        row, head = head, (head + 1) % history
+                    else:
+                        row, k = (head + k) % history, k + 1
+                    S[row].copy_(s_buf); Y[row].copy_(y_buf)
+                    ro[row] = 1.0 / ys
+                    Hdiag = ys / yy
+                if fused:
+                    d = torch.empty_like(g)
+                    self.ops.lbfgs_direction(S, Y, ro, k, head, Hdiag, g, d)
+                else:
+                    # two-loop recursion as tensor expressions (fp64 host-logic tests; vectors beyond one CTA's shared memory)
+                    rows = [(head + i) % history for i in range(k)]
+                    al = [None] * k
+                    q = -g
+                    for i in range(k - 1, -1, -1):
+                        al[i] = torch.dot(S[rows[i]], q) * ro[rows[i]]
+                        q = q - al[i] * Y[rows[i]]
+                    r = q * Hdiag
+                    for i in range(k):
+                        be_i = torch.dot(Y[rows[i]], r) * ro[rows[i]]
+                        r = r + (al[i] - be_i) * S[rows[i]]
+                    d = r
                 t = learning_rate
-            if gtd_h > -tolX:
-                break
+            last = n_iter == max_iter
+            scal = [torch.dot(g, d), d.abs().sum()]
+            x_prev.copy_(x)
             x.add_(d, alpha=t)
-            if n_iter != max_iter:
+            if not last:                                  # eager_lbfgs.py:131: no re-evaluation in the last iteration
                 self.loss_and_grad()
-                g = self.grad.clone()
-                f, gsum = torch.stack((self.loss4[0], g.abs().sum())).tolist()
+                g_new = self.grad.clone()
+                y_buf = g_new - g
+                s_buf = d * t
+                scal += [self.loss4[0], g_new.abs().sum(), torch.dot(y_buf, s_buf), torch.dot(y_buf, y_buf)]
+            vals = torch.stack(scal).tolist()                                      # the iteration's one host sync
+            gtd_h, dsum_h = vals[0], vals[1]
+            if gtd_h > -tolX:                             # no progress along d: the reference breaks BEFORE the step
+                x.copy_(x_prev)
+                if not last:
+                    self.loss_and_grad()
+                break
+            if not last:
+                f, gsum, ys, yy = vals[2:6]
+                g = g_new
             evals += 1
             f_hist.append(f)
             if verbose and (n_iter % 1000 == 0 or n_iter == max_iter):

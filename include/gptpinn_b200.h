@@ -278,6 +278,14 @@ int  gptpinn_sa_tick(int *step_dev, void *stream);
 int  gptpinn_sa_adam(float *p_dev, float *m_dev, float *v_dev, const float *g_dev, long long n, const int *step_dev,
                      double lr, double beta1, double beta2, double eps, int ascent, void *stream);
 
+/* L-BFGS search direction d = -H g from the k most recent (s, y) pairs (the two-loop recursion of eager_lbfgs.py:80-106) in one
+ * launch.  S_dev / Y_dev are rings of `hist` rows of `ld` floats: pair i (i = 0 oldest ... k-1 newest) sits in row (start + i) % hist,
+ * ro_dev[row] = 1 / <y, s> of the pair in that row, Hdiag = <y, s> / <y, y> of the newest pair.  k = 0: d = -Hdiag g.  The vector must
+ * fit one CTA's shared memory: P <= gptpinn_sa_lbfgs_max_params().  16-byte aligned rows (ld % 4 == 0) take the float4 path.      */
+int  gptpinn_sa_lbfgs_max_params(void);
+int  gptpinn_sa_lbfgs_direction(const float *S_dev, const float *Y_dev, const float *ro_dev, int k, int start, int hist, long long ld,
+                                long long P, double Hdiag, const float *g_dev, float *d_dev, void *stream);
+
 /* Host-only (no CUDA call): the work-item plan gptpinn_kg_sweep would build for this grid on a device
  * with n_sm SMs.  sl_hist[l] = number of items with 2^l sibling lanes; *covered = parameters assigned
  * (must equal Np).  Used by tests and for tuning; no reference counterpart.                            */

@@ -92,6 +92,19 @@ def test_lbfgs_equals_the_literal_port_of_eager_lbfgs_cpu():
     m.theta.copy_(theta0)
     fh = m.lbfgs_fit(30, 0.8, history=5, record=True)
     assert np.allclose(fh, fr, rtol=1e-8)
+    # the break statements (eager_lbfgs.py:118-120, 150-174), reached by moving the reference's two tolerances: no progress along
+    # d in the first / a later iteration (the step taken ahead of the test is put back), small gradient, small step, and the
+    # last iteration (no re-evaluation, eager_lbfgs.py:131)
+    early = 0
+    for kw, iters in ((dict(tolX=1e30), 20), (dict(tolFun=1e30), 20), (dict(tolFun=5000.0), 30), (dict(tolFun=1000.0), 30), (dict(tolX=0.5), 30),
+                      (dict(tolX=5.0), 30), (dict(), 1), (dict(), 2), (dict(), 3)):
+        xr, fr = R.lbfgs_reference(opfunc, theta0.clone(), iters, 0.8, history=7, **kw)
+        m.theta.copy_(theta0)
+        fh = m.lbfgs_fit(iters, 0.8, history=7, record=True, **kw)
+        assert len(fh) == len(fr) and np.allclose(fh, fr, rtol=1e-9), (kw, iters, len(fh), len(fr))
+        assert float((m.theta - xr).abs().max()) < 1e-12, (kw, iters)
+        early += len(fh) < iters + 1
+    assert early == 6
 
 
 def test_sa_pinn_has_no_cpu_path():
@@ -226,3 +239,61 @@ def test_tf_free_allen_cahn_driver_writes_the_reference_result_files(tmp_path):
     p = np.load(out / "params.npy", allow_pickle=True).item()
     assert p["parameter size"] == 121 and p["layers_pinn"] == [2, 128, 128, 128, 128, 1]
     assert r["sa_final"][0][0] < 50.0            # 200 Adam + 40 L-BFGS steps already pull the weighted loss far below its start (~1e3)
+
+
+@pytest.mark.gpu
+def test_fused_lbfgs_direction_equals_the_two_loop_recursion_gpu():
+    """gptpinn_sa_lbfgs_direction (one launch) against the two-loop recursion of eager_lbfgs.py:80-106 evaluated in fp64 on the
+    same fp32 history (the dot-product order differs, so not bitwise): k = 0, a partly filled and a full ring, a ring that
+    wraps, the reference-size vector (50 049 weights), 16-byte aligned rows (float4 path; from 8192 weights on the cluster
+    kernel, with and without a scalar tail) and unaligned ones (scalar path);
+    then a whole L-BFGS run with the kernel and with tensor expressions."""
+    from gptpinn import GptPinnError
+    from gptpinn.sa_pinn import CudaOps, SAPinn
+    dev = torch.device("cuda")
+    cu = CudaOps(dev)
+    assert cu.lbfgs_capacity() >= 50049
+    gen = torch.Generator().manual_seed(3)
+    for P, hist, k, start, pad in ((50049, 50, 50, 0, True), (50049, 50, 50, 17, True), (50049, 50, 7, 46, False), (1234, 5, 0, 0, True),
+                                   (777, 256, 256, 255, False), (31, 3, 2, 2, True), (4100, 6, 6, 3, True), (4099, 6, 1, 5, True),
+                                   (8195, 4, 4, 1, True), (8193, 9, 5, 7, True), (cu.lbfgs_capacity(), 3, 3, 0, True)):
+        S = torch.randn(hist, P, generator=gen, dtype=torch.float64) * 1e-2
+        Y = S * (0.5 + torch.rand(hist, P, generator=gen, dtype=torch.float64)) + 1e-4 * torch.randn(hist, P, generator=gen, dtype=torch.float64)
+        g = torch.randn(P, generator=gen, dtype=torch.float64)
+        ld = (P + 3) & ~3 if pad else P
+        S32 = torch.zeros(hist, ld, dtype=torch.float32, device=dev)[:, :P]
+        Y32 = torch.zeros(hist, ld, dtype=torch.float32, device=dev)[:, :P]
+        S32.copy_(S); Y32.copy_(Y)
+        g32 = g.to(dev, torch.float32)
+        Sd, Yd = S32.double(), Y32.double()
+        ro32 = (1.0 / (Sd * Yd).sum(1)).float()
+        rows = [(start + i) % hist for i in range(k)]
+        Hd = float((Sd[rows[-1]] * Yd[rows[-1]]).sum() / (Yd[rows[-1]] ** 2).sum()) if k else 0.37
+        q = -g32.double()
+        al = [None] * k
+        for i in range(k - 1, -1, -1):
+            al[i] = torch.dot(Sd[rows[i]], q) * ro32[rows[i]].double()
+            q = q - al[i] * Yd[rows[i]]
+        r = q * float(np.float32(Hd))
+        for i in range(k):
+            r = r + (al[i] - torch.dot(Yd[rows[i]], r) * ro32[rows[i]].double()) * Sd[rows[i]]
+        d = torch.full((P,), float("nan"), dtype=torch.float32, device=dev)
+        cu.lbfgs_direction(S32, Y32, ro32, k, start, Hd, g32, d)
+        d2 = torch.empty_like(d)
+        cu.lbfgs_direction(S32, Y32, ro32, k, start, Hd, g32, d2)
+        torch.cuda.synchronize()
+        assert torch.equal(d, d2)                                                     # fixed summation order
+        err = float((d.double() - r).norm() / r.norm())
+        assert err < 2e-5, (P, hist, k, start, pad, err)      # fp32 rounding of 2k chained projections
+    with pytest.raises(GptPinnError):
+        big = torch.zeros(cu.lbfgs_capacity() + 1, dtype=torch.float32, device=dev)
+        cu.lbfgs_direction(big[None], big[None], big[:1], 1, 0, 1.0, big, big.clone())
+    prob = _problem(1500, 96, 40, torch.float32, device=dev, seed=9)
+    a = SAPinn([2, 48, 48, 1], *prob, 5.5e-4, 3.0, seed=2)
+    a.adam_fit(100)
+    th = a.theta.clone()
+    fa = a.lbfgs_fit(25, 0.8, history=6, record=True, use_fused=True)
+    a.theta.copy_(th)
+    fb = a.lbfgs_fit(25, 0.8, history=6, record=True, use_fused=False)
+    n = min(len(fa), len(fb), 10)
+    assert n >= 5 and np.allclose(fa[:n], fb[:n], rtol=2e-3)     # fixed-step L-BFGS amplifies rounding; the early iterations agree
