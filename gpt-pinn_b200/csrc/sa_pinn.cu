@@ -368,6 +368,181 @@ sa_lbfgs_direction_cluster_kernel(const float *__restrict__ S, const float *__re
     for (int e = tid; e < nt; e += LBC_THREADS) d[t0 + e] = qt[e];
 }
 
+
+// ---- weight-gradient contraction  out[j][i] = sum_r G[r][j] A[r][i]  over R = 4N rows (AC_main.py:268-272, the tape's dW) ----------
+// A [W x R] x [R x W] product with R ~ 8*10^4 and W = 128: the library's split-K kernel ran it at 17 TFLOP/s (a third of the
+// reverse pass).  Here the ROWS are cut into one chunk per CTA (2 CTAs per SM); a CTA streams its chunk through a double-buffered
+// shared-memory stage (cp.async, 16 rows of both matrices per stage) and keeps the whole 128 x 128 product in registers: thread
+// (ty, tx) of 16 x 16 owns the 8 x 8 outputs {4 ty .. 4 ty + 3, 64 + 4 ty ..} x {4 tx .. 4 tx + 3, 64 + 4 tx ..} -- four LDS.128
+// (two of them warp-wide broadcasts, none with a bank conflict) per 64 FMAs.  The CTA partials go to a workspace and are summed
+// in a fixed order by sa_sum_partials_kernel (no atomics: bitwise reproducible).  W < 128 runs zero-padded (tests, small nets).
+constexpr int WG_THREADS = 256, WG_KT = 16, WG_W = 128, WG_GRID = 296;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(WG_THREADS, 2)
+sa_wgrad_kernel(const float *__restrict__ G, const float *__restrict__ A, long long R, int W, int fast, float *__restrict__ partial)
+{
+    __shared__ __align__(16) float Gs[2][WG_KT][WG_W], As[2][WG_KT][WG_W];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const long long chunk = (R + gridDim.x - 1) / gridDim.x;
+    const long long r0 = (long long)blockIdx.x * chunk, r1 = min(R, r0 + chunk);
+    const int ntiles = r1 > r0 ? (int)((r1 - r0 + WG_KT - 1) / WG_KT) : 0;
+    float acc[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+
+    auto load_tile = [&](int t, int buf) {
+        const long long base = r0 + (long long)t * WG_KT;
+        if (fast) {                                   // W == 128, 16-byte aligned: a row is 32 float4, a full tile 512 per matrix
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int e = tid + h * WG_THREADS, rr = e >> 5, c4 = e & 31;
+                const long long row = base + rr;
+                if (row < r1) {
+                    cp_async16(&Gs[buf][rr][4 * c4], G + row * WG_W + 4 * c4);
+                    cp_async16(&As[buf][rr][4 * c4], A + row * WG_W + 4 * c4);
+                } else {
+                    *reinterpret_cast<float4 *>(&Gs[buf][rr][4 * c4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4 *>(&As[buf][rr][4 * c4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        } else {                                      // any W <= 128: zero-padded columns / rows
+            for (int e = tid; e < WG_KT * WG_W; e += WG_THREADS) {
+                const int rr = e >> 7, c = e & 127;
+                const long long row = base + rr;
+                const bool ok = row < r1 && c < W;
+                Gs[buf][rr][c] = ok ? G[row * W + c] : 0.f;
+                As[buf][rr][c] = ok ? A[row * W + c] : 0.f;
+            }
+        }
+        cp_async_commit();
+    };
+
+    if (ntiles > 0) load_tile(0, 0);
+    for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        if (t + 1 < ntiles) { load_tile(t + 1, buf ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = 0; kk < WG_KT; ++kk) {
+            const float4 g0 = *reinterpret_cast<const float4 *>(&Gs[buf][kk][4 * ty]), g1 = *reinterpret_cast<const float4 *>(&Gs[buf][kk][64 + 4 * ty]);
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][kk][4 * tx]), a1 = *reinterpret_cast<const float4 *>(&As[buf][kk][64 + 4 * tx]);
+            const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(gv[a], av[b], acc[a][b]);
+        }
+        __syncthreads();                              // the stage just read is refilled by the next iteration's loads
+    }
+    float *dst = partial + (size_t)blockIdx.x * (WG_W * WG_W);
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int j = (a < 4 ? 4 * ty + a : 64 + 4 * ty + (a - 4));
+        *reinterpret_cast<float4 *>(dst + j * WG_W + 4 * tx) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+        *reinterpret_cast<float4 *>(dst + j * WG_W + 64 + 4 * tx) = make_float4(acc[a][4], acc[a][5], acc[a][6], acc[a][7]);
+    }
+}
+
+// out[j * out_ld + i] = sum_b partial[b * part_stride + j * src_ld + i] in a fixed order: four threads per output take the parts
+// b = 0, 4, 8, ... / 1, 5, ... / ..., two running sums each, combined through shared memory as ((t0 + t1) + (t2 + t3))
+constexpr int SP_OUT = 64;                                   // outputs per CTA (256 threads)
+
+__global__ void __launch_bounds__(4 * SP_OUT) sa_sum_partials_kernel(const float *__restrict__ partial, int nparts, long long part_stride, int rows,
+                                                                     int cols, int src_ld, float *__restrict__ out, int out_ld)
+{
+    __shared__ float red[4][SP_OUT];
+    const int sub = threadIdx.x / SP_OUT, o = threadIdx.x % SP_OUT;
+    const int e = blockIdx.x * SP_OUT + o;
+    const bool live = e < rows * cols;
+    const int j = live ? e / cols : 0, i = live ? e % cols : 0;
+    const float *src = partial + (size_t)j * src_ld + i;
+    float s0 = 0.f, s1 = 0.f;
+    if (live) {
+        int b = sub;
+        for (; b + 4 < nparts; b += 8) { s0 += src[(size_t)b * part_stride]; s1 += src[(size_t)(b + 4) * part_stride]; }
+        if (b < nparts) s0 += src[(size_t)b * part_stride];
+    }
+    red[sub][o] = s0 + s1;
+    __syncthreads();
+    if (sub == 0 && live) out[(size_t)j * out_ld + i] = (red[0][o] + red[1][o]) + (red[2][o] + red[3][o]);
+}
+
+// ---- column sums over the points (bias gradients; the first map's weight gradient) -------------------------------------------------
+// G is [4][N][W].  L0 = false: part[b][0][c] = sum over the CTA's rows of G[0][r][c] (the bias gradient of a hidden->hidden map).
+// L0 = true (the first map, inputs (x, t) with channels (x,1,0,0) and (t,0,1,0)): also part[b][1][c] = sum x_r G[0][r][c] + G[1][r][c]
+// and part[b][2][c] = sum t_r G[0][r][c] + G[2][r][c].  Thread = (row lane, column), rows strided over the row lanes.
+constexpr int CS_THREADS = 256, CS_GRID = 592;
+
+template <bool L0>
+__global__ void __launch_bounds__(CS_THREADS) sa_colsums_kernel(const float *__restrict__ G, const float *__restrict__ xt, long long N, int W,
+                                                                float *__restrict__ part)
+{
+    __shared__ float red[3][CS_THREADS];
+    const int tid = threadIdx.x;
+    const int lanes = CS_THREADS / W;                 // W <= 256
+    const int rl = tid / W, c = tid % W;
+    const long long chunk = (N + gridDim.x - 1) / gridDim.x;
+    const long long r0 = (long long)blockIdx.x * chunk, r1 = min(N, r0 + chunk);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    if (rl < lanes) {
+        const float *G0 = G, *G1 = G + N * W, *G2 = G + 2 * N * W;
+#pragma unroll 4
+        for (long long r = r0 + rl; r < r1; r += lanes) {
+            const float g0 = G0[r * W + c];
+            s0 += g0;
+            if (L0) {
+                s1 += fmaf(xt[2 * r], g0, G1[r * W + c]);
+                s2 += fmaf(xt[2 * r + 1], g0, G2[r * W + c]);
+            }
+        }
+    }
+    red[0][tid] = s0; red[1][tid] = s1; red[2][tid] = s2;
+    __syncthreads();
+    if (tid < W) {
+        for (int l = 1; l < lanes; ++l) { s0 += red[0][l * W + tid]; s1 += red[1][l * W + tid]; s2 += red[2][l * W + tid]; }
+        float *dst = part + (size_t)blockIdx.x * 3 * W;
+        dst[tid] = s0;
+        if (L0) { dst[W + tid] = s1; dst[2 * W + tid] = s2; }
+    }
+}
+
+// sums the CTA partials: one warp per column, lane l takes the parts l, l + 32, ... and a fixed shuffle tree combines the lanes;
+// L0: gb0[c], gW0[c][0], gW0[c][1] (nn.Linear layout [out][in] of the first map)
+template <bool L0>
+__global__ void __launch_bounds__(256) sa_colsums_final_kernel(const float *__restrict__ part, int nparts, int W, float *__restrict__ gb,
+                                                               float *__restrict__ gW0)
+{
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (c >= W) return;                                       // (whole warps leave together)
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int b = lane; b < nparts; b += 32) {
+        const float *src = part + (size_t)b * 3 * W;
+        s0 += src[c];
+        if (L0) { s1 += src[W + c]; s2 += src[2 * W + c]; }
+    }
+    for (int off = 16; off; off >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+        if (L0) { s1 += __shfl_xor_sync(0xffffffffu, s1, off); s2 += __shfl_xor_sync(0xffffffffu, s2, off); }
+    }
+    if (lane == 0) {
+        gb[c] = s0;
+        if (L0) { gW0[2 * c] = s1; gW0[2 * c + 1] = s2; }
+    }
+}
+
 }  // namespace gp
 
 using namespace gp;
@@ -482,6 +657,48 @@ extern "C" int gptpinn_sa_lbfgs_direction(const float *S_dev, const float *Y_dev
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return GPTPINN_E_CUDA;
     kern<<<1, gp::LB_THREADS, smem, (cudaStream_t)stream>>>(S_dev, Y_dev, ro_dev, k, k > 0 ? start : 0, k > 0 ? hist : 1, ld, (int)P, (float)Hdiag,
                                                            g_dev, d_dev);
+    SA_LAUNCHED();
+    return GPTPINN_OK;
+}
+
+extern "C" long long gptpinn_sa_workspace_floats(void)
+{
+    return (long long)gp::WG_GRID * gp::WG_W * gp::WG_W;        // (the column-sum partials, CS_GRID * 3 * 256 floats, fit as well)
+}
+
+extern "C" int gptpinn_sa_wgrad(const float *G_dev, const float *A_dev, long long R, int W, float *out_dev, float *workspace_dev, void *stream)
+{
+    SA_CHECK(G_dev && A_dev && out_dev && workspace_dev && R > 0 && W > 0 && W <= gp::WG_W, "gptpinn_sa_wgrad");
+    const long long tiles = (R + gp::WG_KT - 1) / gp::WG_KT;
+    const int grid = (int)(tiles < gp::WG_GRID ? tiles : gp::WG_GRID);
+    const int fast = W == gp::WG_W && ((reinterpret_cast<uintptr_t>(G_dev) | reinterpret_cast<uintptr_t>(A_dev)) & 15u) == 0;
+    gp::sa_wgrad_kernel<<<grid, gp::WG_THREADS, 0, (cudaStream_t)stream>>>(G_dev, A_dev, R, W, fast, workspace_dev);
+    SA_LAUNCHED();
+    gp::sa_sum_partials_kernel<<<(W * W + gp::SP_OUT - 1) / gp::SP_OUT, 4 * gp::SP_OUT, 0, (cudaStream_t)stream>>>(
+        workspace_dev, grid, (long long)gp::WG_W * gp::WG_W, W, W, gp::WG_W, out_dev, W);
+    SA_LAUNCHED();
+    return GPTPINN_OK;
+}
+
+extern "C" int gptpinn_sa_bias_grad(const float *G_dev, long long N, int W, float *gb_dev, float *workspace_dev, void *stream)
+{
+    SA_CHECK(G_dev && gb_dev && workspace_dev && N > 0 && W > 0 && W <= gp::CS_THREADS, "gptpinn_sa_bias_grad");
+    const int grid = (int)(N < gp::CS_GRID ? N : gp::CS_GRID);
+    gp::sa_colsums_kernel<false><<<grid, gp::CS_THREADS, 0, (cudaStream_t)stream>>>(G_dev, nullptr, N, W, workspace_dev);
+    SA_LAUNCHED();
+    gp::sa_colsums_final_kernel<false><<<(W + 7) / 8, 256, 0, (cudaStream_t)stream>>>(workspace_dev, grid, W, gb_dev, nullptr);
+    SA_LAUNCHED();
+    return GPTPINN_OK;
+}
+
+extern "C" int gptpinn_sa_layer0_grad(const float *G_dev, const float *xt_dev, long long N, int W, float *gW0_dev, float *gb0_dev,
+                                      float *workspace_dev, void *stream)
+{
+    SA_CHECK(G_dev && xt_dev && gW0_dev && gb0_dev && workspace_dev && N > 0 && W > 0 && W <= gp::CS_THREADS, "gptpinn_sa_layer0_grad");
+    const int grid = (int)(N < gp::CS_GRID ? N : gp::CS_GRID);
+    gp::sa_colsums_kernel<true><<<grid, gp::CS_THREADS, 0, (cudaStream_t)stream>>>(G_dev, xt_dev, N, W, workspace_dev);
+    SA_LAUNCHED();
+    gp::sa_colsums_final_kernel<true><<<(W + 7) / 8, 256, 0, (cudaStream_t)stream>>>(workspace_dev, grid, W, gb0_dev, gW0_dev);
     SA_LAUNCHED();
     return GPTPINN_OK;
 }

@@ -79,7 +79,8 @@ EXPORTS = ("gptpinn_version", "gptpinn_last_error", "gptpinn_create", "gptpinn_d
            "gptpinn_pinn_train_batch",
            "gptpinn_sa_layer0", "gptpinn_sa_act_forward", "gptpinn_sa_act_backward", "gptpinn_sa_output_forward",
            "gptpinn_sa_loss_workspace_floats", "gptpinn_sa_loss", "gptpinn_sa_output_backward", "gptpinn_sa_tick", "gptpinn_sa_adam",
-           "gptpinn_sa_lbfgs_max_params", "gptpinn_sa_lbfgs_direction")
+           "gptpinn_sa_lbfgs_max_params", "gptpinn_sa_lbfgs_direction", "gptpinn_sa_workspace_floats", "gptpinn_sa_wgrad",
+           "gptpinn_sa_bias_grad", "gptpinn_sa_layer0_grad")
 
 _lib = None
 
@@ -99,6 +100,7 @@ def lib():
             "or `make -C gpt-pinn_b200/csrc`.  There is no CPU / PyTorch fallback.")
     L = C.CDLL(LIB_PATH)
     L.gptpinn_version.restype = C.c_int
+    L.gptpinn_sa_workspace_floats.restype = C.c_longlong
     L.gptpinn_last_error.restype = C.c_char_p
     L.gptpinn_create.argtypes = [C.POINTER(C.c_void_p)]
     L.gptpinn_destroy.argtypes = [C.c_void_p]

@@ -36,6 +36,7 @@ class CudaOps:
         L = _lib.lib()
         self.L = L
         self.ws = torch.zeros(int(L.gptpinn_sa_loss_workspace_floats()), dtype=torch.float32, device=device)
+        self.ws2 = torch.empty(int(L.gptpinn_sa_workspace_floats()), dtype=torch.float32, device=device)     # wgrad / column-sum partials
 
     def _s(self):
         return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
@@ -71,6 +72,25 @@ class CudaOps:
 
     def tick(self, step):
         _lib.check(self.L.gptpinn_sa_tick(self._p(step), self._s()), "gptpinn_sa_tick")
+
+    def wgrad(self, G, A, out):
+        """out[j][i] = sum over channels and points of G[c][r][j] A[c][r][i]: the weight gradient of a hidden->hidden map"""
+        W = G.shape[2]
+        if W > 128:                                   # wider than the kernel's register tile: library GEMM
+            torch.mm(G.view(-1, W).t(), A.view(-1, W), out=out)
+            return
+        _lib.check(self.L.gptpinn_sa_wgrad(self._p(G), self._p(A), C.c_longlong(G.shape[0] * G.shape[1]), C.c_int(W), self._p(out),
+                                           self._p(self.ws2), self._s()), "gptpinn_sa_wgrad")
+
+    def bias_grad(self, G, gb):
+        """gb[j] = sum over the points of G[0][r][j]"""
+        _lib.check(self.L.gptpinn_sa_bias_grad(self._p(G), C.c_longlong(G.shape[1]), C.c_int(G.shape[2]), self._p(gb), self._p(self.ws2), self._s()),
+                   "gptpinn_sa_bias_grad")
+
+    def layer0_grad(self, G, xt, gW0, gb0):
+        """gradients of the first map from the adjoints of its pre-activations (inputs (x, t), channels (x,1,0,0) / (t,0,1,0))"""
+        _lib.check(self.L.gptpinn_sa_layer0_grad(self._p(G), self._p(xt), C.c_longlong(G.shape[1]), C.c_int(G.shape[2]), self._p(gW0), self._p(gb0),
+                                                 self._p(self.ws2), self._s()), "gptpinn_sa_layer0_grad")
 
     def lbfgs_capacity(self):
         return int(self.L.gptpinn_sa_lbfgs_max_params())
@@ -148,7 +168,6 @@ class SAPinn:
         self.U, self.Ubar = z(4, N), z(4, N)
         self.gwf, self.gwu = z(self.NR), z(self.NI)
         self.loss4 = z(4)
-        self.tmpW = z(W)
         self.step = torch.zeros(1, dtype=torch.int32, device=dev)
         self.m_t, self.v_t = z(self.P), z(self.P)
         self.m_f, self.v_f = z(self.NR), z(self.NR)
@@ -173,17 +192,13 @@ class SAPinn:
         o.output_backward(self.Ubar, self.Wv[NH], G)
         for l in range(NH - 1, -1, -1):
             o.act_backward(self.Z[l], G)
-            torch.sum(G[0], dim=0, out=self.gb[l])
             if l > 0:
-                torch.mm(G.view(4 * N, W).t(), self.A[l - 1].view(4 * N, W), out=self.gW[l])
+                o.bias_grad(G, self.gb[l])
+                o.wgrad(G, self.A[l - 1], self.gW[l])
                 torch.mm(G.view(4 * N, W), self.Wv[l], out=G2.view(4 * N, W))
                 G, G2 = G2, G
             else:
-                # first map: inputs (x, t) with channels (x,1,0,0) and (t,0,1,0)
-                torch.mv(G[0].t(), self.xt[:, 0], out=self.tmpW)
-                torch.add(self.tmpW, torch.sum(G[1], dim=0), out=self.gW[0][:, 0])
-                torch.mv(G[0].t(), self.xt[:, 1], out=self.tmpW)
-                torch.add(self.tmpW, torch.sum(G[2], dim=0), out=self.gW[0][:, 1])
+                o.layer0_grad(G, self.xt, self.gW[0], self.gb[0])
         return self.loss4
 
     # ------------------------------------------------------------------ Adam phase (AC_main.py:282-298)

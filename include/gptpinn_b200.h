@@ -278,6 +278,18 @@ int  gptpinn_sa_tick(int *step_dev, void *stream);
 int  gptpinn_sa_adam(float *p_dev, float *m_dev, float *v_dev, const float *g_dev, long long n, const int *step_dev,
                      double lr, double beta1, double beta2, double eps, int ascent, void *stream);
 
+/* Weight-gradient contraction of a hidden->hidden map over all channels and points (the tape's dW of AC_main.py:268-272):
+ * out[j][i] = sum_r G[r][j] A[r][i], G / A row-major [R][W] (R = 4 N rows), out row-major [W][W]; W <= 128.  Row chunks per CTA,
+ * partial products in workspace_dev (gptpinn_sa_workspace_floats() floats), summed in a fixed order.                                */
+long long gptpinn_sa_workspace_floats(void);
+int  gptpinn_sa_wgrad(const float *G_dev, const float *A_dev, long long R, int W, float *out_dev, float *workspace_dev, void *stream);
+/* Bias gradient of a map: gb[c] = sum_r G[0][r][c] over the N points (G is [4][N][W]); W <= 256.                                     */
+int  gptpinn_sa_bias_grad(const float *G_dev, long long N, int W, float *gb_dev, float *workspace_dev, void *stream);
+/* Gradients of the first map (inputs (x, t) with channels (x,1,0,0), (t,0,1,0)): gb0[c] = sum_r G[0][r][c],
+ * gW0[c][0] = sum_r x_r G[0][r][c] + G[1][r][c], gW0[c][1] = sum_r t_r G[0][r][c] + G[2][r][c]; xt_dev is [N][2]; W <= 256.           */
+int  gptpinn_sa_layer0_grad(const float *G_dev, const float *xt_dev, long long N, int W, float *gW0_dev, float *gb0_dev,
+                            float *workspace_dev, void *stream);
+
 /* L-BFGS search direction d = -H g from the k most recent (s, y) pairs (the two-loop recursion of eager_lbfgs.py:80-106) in one
  * launch.  S_dev / Y_dev are rings of `hist` rows of `ld` floats: pair i (i = 0 oldest ... k-1 newest) sits in row (start + i) % hist,
  * ro_dev[row] = 1 / <y, s> of the pair in that row, Hdiag = <y, s> / <y, y> of the newest pair.  k = 0: d = -Hdiag g.  The vector must

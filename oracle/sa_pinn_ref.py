@@ -115,6 +115,19 @@ class TorchOps:
     def output_backward(self, Ubar, Wout, G):
         G[:] = Ubar[:, :, None] * Wout.reshape(1, 1, -1)
 
+    def wgrad(self, G, A, out):
+        W = G.shape[2]
+        out[:] = G.reshape(-1, W).t() @ A.reshape(-1, W)
+
+    def bias_grad(self, G, gb):
+        gb[:] = G[0].sum(0)
+
+    def layer0_grad(self, G, xt, gW0, gb0):
+        # first map: inputs (x, t) with channels (x,1,0,0) and (t,0,1,0)
+        gb0[:] = G[0].sum(0)
+        gW0[:, 0] = G[0].t() @ xt[:, 0] + G[1].sum(0)
+        gW0[:, 1] = G[0].t() @ xt[:, 1] + G[2].sum(0)
+
     def tick(self, step):
         step += 1
 

@@ -159,6 +159,28 @@ def test_every_sa_kernel_matches_the_torch_recurrences_gpu():
     cu.output_backward(outs_c[0], Wout.to(dev), Gc2)
     th.output_backward(outs_c[0].cpu().double(), Wout.double(), Gt2)
     assert torch.allclose(Gc2.cpu().double(), Gt2, rtol=1e-6, atol=1e-9)
+    # weight / bias gradient contractions: the register-tile kernel (W = 128, aligned), its zero-padded path (W < 128, ragged
+    # row counts, fewer row tiles than CTAs), the library fallback (W > 128), against float64 sums of the same fp32 inputs
+    for Nn, Ww in ((777, 128), (5003, 128), (20712, 128), (7, 128), (333, 48), (1, 12), (90, 160)):
+        Gg, Aa = r(4, Nn, Ww).to(dev), r(4, Nn, Ww).to(dev)
+        xy = (torch.rand(Nn, 2, generator=g) * 2 - 1).to(dev)
+        oc, ot = torch.full((Ww, Ww), float("nan"), device=dev), torch.zeros(Ww, Ww, dtype=torch.float64)
+        cu.wgrad(Gg, Aa, oc)
+        th.wgrad(Gg.cpu().double(), Aa.cpu().double(), ot)
+        oc2 = torch.empty_like(oc)
+        cu.wgrad(Gg, Aa, oc2)
+        assert torch.equal(oc, oc2) or Ww > 128                                            # fixed summation order
+        assert float((oc.cpu().double() - ot).abs().max()) < 2e-6 * (4 * Nn) ** 0.5 * 4 + 1e-6, (Nn, Ww)
+        bc, bt_ = torch.full((Ww,), float("nan"), device=dev), torch.zeros(Ww, dtype=torch.float64)
+        cu.bias_grad(Gg, bc)
+        th.bias_grad(Gg.cpu().double(), bt_)
+        assert float((bc.cpu().double() - bt_).abs().max()) < 2e-6 * Nn ** 0.5 * 4 + 1e-6, (Nn, Ww)
+        wc, wt_ = torch.full((Ww, 2), float("nan"), device=dev), torch.zeros(Ww, 2, dtype=torch.float64)
+        bc2, bt2 = torch.full((Ww,), float("nan"), device=dev), torch.zeros(Ww, dtype=torch.float64)
+        cu.layer0_grad(Gg, xy, wc, bc2)
+        th.layer0_grad(Gg.cpu().double(), xy.cpu().double(), wt_, bt2)
+        assert torch.equal(bc, bc2)
+        assert float((wc.cpu().double() - wt_).abs().max()) < 2e-6 * Nn ** 0.5 * 8 + 1e-6, (Nn, Ww)
     # Keras Adam, descent and ascent, three consecutive steps (device-side step counter)
     n = 5001
     p, gr = r(n), r(n)
@@ -207,7 +229,7 @@ def test_sa_fit_graph_replay_equals_eager_and_training_makes_progress_gpu():
     assert torch.allclose(ra, rb, rtol=1e-4) and torch.allclose(a.theta, b.theta, atol=1e-5)      # same kernels, same order
     assert int(a.step.item()) == 60 and float(ra[-1]) < float(ra[0])
     assert float(a.wf.mean()) > 0.5 - 0.05 and float((a.wf - b.wf).abs().max()) < 1e-4
-    f_hist = a.lbfgs_fit(80, 0.8, record=True)
+    f_hist = a.lbfgs_fit(40, 0.8, record=True)       # (the fixed-step iteration is erratic later on: isolated loss spikes of 10-100x in fp64 as well)
     assert len(f_hist) >= 2 and np.isfinite(f_hist).all() and min(f_hist) < f_hist[0]
     w, bb = a.weights_for_P()
     assert [tuple(x.shape) for x in w] == [(64, 2), (64, 64), (64, 64), (1, 64)] and [tuple(x.shape) for x in bb] == [(64,), (64,), (64,), (1,)]
