@@ -60,6 +60,28 @@ def _chunks(n):
     return [(cuts[i], cuts[i + 1]) for i in range(k) if cuts[i + 1] > cuts[i]]
 
 
+def _trained(mine, layers_pinn, xt_resid, IC_xt, IC_u, BC_xt, BC_u, f_hat, epochs_pinn, lr_pinn, tol):
+    """The tolerance-stopped full PINNs of this rank's test parameters, trained once per (parameters, data, epochs, lr, tol):
+    pinn_test and pinn_test_loss ask for the same trainings (see gptpinn.pinn: memo of finished test-set trainings).  Per
+    parameter: the trained network, the iterations entered, and the loss at the top of every iteration."""
+    chunks = _chunks(len(mine))
+    tensors = (xt_resid, IC_xt, IC_u, BC_xt, BC_u, f_hat)
+    key = pinn.train_memo_key("burgers", layers_pinn, mine, epochs_pinn, lr_pinn, tol, chunks, tensors)
+    recs = pinn.train_memo_get(key)
+    if recs is not None:
+        return recs
+    recs = []
+    for a, b in chunks:
+        nets = [NN(layers_pinn, mine[k]).to(device) for k in range(a, b)]
+        res = pinn.train_fused_batch(nets, "burgers", [(mine[k],) for k in range(a, b)], xt_resid, f_hat, IC_xt, IC_u, None,
+                                     BC_xt, BC_u, epochs_pinn, lr_pinn, tol=tol, trace_every=1)
+        for net, r in zip(nets, res):
+            done = pinn.epochs_done(r)                                   # iterations entered
+            recs.append(dict(net=net, done=done, trace=r["trace"][:max(done, 1)].cpu().numpy().astype(np.float64)))
+    pinn.train_memo_put(key, tensors, recs)
+    return recs
+
+
 def pinn_test(b_test, layers_pinn, xt_resid, IC_xt, IC_u, BC_xt, BC_u, f_hat,
               epochs_pinn, lr_pinn, xt_test, tol):
     """One tolerance-stopped full PINN per test parameter (B_test.py:116-149), fused training kernel, several
@@ -67,15 +89,11 @@ def pinn_test(b_test, layers_pinn, xt_resid, IC_xt, IC_u, BC_xt, BC_u, f_hat,
     b_test = np.asarray(b_test, dtype=np.float64).reshape(-1)
     t0 = time.time()
     lo, hi = offline.shard_bounds(len(b_test))
-    mine = b_test[lo:hi]
+    recs = _trained(b_test[lo:hi], layers_pinn, xt_resid, IC_xt, IC_u, BC_xt, BC_u, f_hat, epochs_pinn, lr_pinn, tol)
     local = torch.zeros((hi - lo, xt_test.shape[0]), dtype=torch.float32, device=xt_test.device)
-    for a, b in _chunks(len(mine)):
-        nets = [NN(layers_pinn, mine[k]).to(device) for k in range(a, b)]
-        pinn.train_fused_batch(nets, "burgers", [(mine[k],) for k in range(a, b)], xt_resid, f_hat, IC_xt, IC_u, None,
-                               BC_xt, BC_u, epochs_pinn, lr_pinn, tol=tol)
-        with torch.no_grad():
-            for k, net in zip(range(a, b), nets):
-                local[k] = net(xt_test)[:, 0]
+    with torch.no_grad():
+        for k, rec in enumerate(recs):
+            local[k] = rec["net"](xt_test)[:, 0]
     pinn_soln = offline.gather_rows(local, len(b_test)).t().cpu().numpy().astype(np.float64)
     return offline.spread_hours(time.time() - t0, len(b_test)), pinn_soln
 
@@ -87,23 +105,18 @@ def pinn_test_loss(b_test, layers_pinn, xt_resid, IC_xt, IC_u, BC_xt, BC_u,
     loss goes into the first still-zero slot."""
     b_test = np.asarray(b_test, dtype=np.float64).reshape(-1)
     lo, hi = offline.shard_bounds(len(b_test))
-    mine = b_test[lo:hi]
+    recs = _trained(b_test[lo:hi], layers_pinn, xt_resid, IC_xt, IC_u, BC_xt, BC_u, f_hat, epochs_pinn, lr_pinn, tol)
     local = np.zeros((hi - lo, 61))
-    for a, b in _chunks(len(mine)):
-        nets = [NN(layers_pinn, mine[k]).to(device) for k in range(a, b)]
-        res = pinn.train_fused_batch(nets, "burgers", [(mine[k],) for k in range(a, b)], xt_resid, f_hat, IC_xt, IC_u, None,
-                                     BC_xt, BC_u, epochs_pinn, lr_pinn, tol=tol, trace_every=1)
-        for k, r in zip(range(a, b), res):
-            done = pinn.epochs_done(r)                                   # iterations entered
-            tr = r["trace"].cpu().numpy().astype(np.float64)             # tr[j-1] = loss at the top of iteration j
-            col = local[k]
-            if done >= 1:
-                col[0] = tr[0]
-            stopped = tol is not None and done >= 1 and tr[done - 1] < tol
-            for j in range(1, done + 1):
-                if (j % 1000 == 0) or (j == epochs_pinn):
-                    col[int(j / 1000)] = tr[j - 1]
-            if stopped:
-                col[np.where(col == 0)[0][0]] = tr[done - 1]
+    for k, rec in enumerate(recs):
+        done, tr = rec["done"], rec["trace"]                              # tr[j-1] = loss at the top of iteration j
+        col = local[k]
+        if done >= 1:
+            col[0] = tr[0]
+        stopped = tol is not None and done >= 1 and tr[done - 1] < tol
+        for j in range(1, done + 1):
+            if (j % 1000 == 0) or (j == epochs_pinn):
+                col[int(j / 1000)] = tr[j - 1]
+        if stopped:
+            col[np.where(col == 0)[0][0]] = tr[done - 1]
     out = offline.gather_rows(torch.from_numpy(local).to(xt_resid.device), len(b_test))
     return out.t().cpu().numpy().astype(np.float64)

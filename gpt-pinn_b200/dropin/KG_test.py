@@ -57,6 +57,31 @@ def _chunks(n):
     return [(cuts[i], cuts[i + 1]) for i in range(k) if cuts[i + 1] > cuts[i]]
 
 
+def _trained(mine, layers_pinn, xcos_x2cos2, xt_resid, IC_xt, IC_u1, IC_u2, BC_xt, BC_u, f_hat, epochs_pinn, lr_pinn):
+    """The full PINNs of this rank's test parameters, trained once per (parameters, data, epochs, lr): pinn_test and
+    pinn_test_loss ask for the same trainings (see gptpinn.pinn: memo of finished test-set trainings).  Per parameter:
+    the trained network, the loss before the step of epochs 1, 1001, 2001, ... and the loss after the last step."""
+    chunks = _chunks(len(mine))
+    tensors = (xcos_x2cos2, xt_resid, IC_xt, IC_u1, IC_u2, BC_xt, BC_u, f_hat)
+    key = pinn.train_memo_key("kg", layers_pinn, mine, epochs_pinn, lr_pinn, None, chunks, tensors)
+    recs = pinn.train_memo_get(key)
+    if recs is not None:
+        return recs
+    recs = []
+    for a, b in chunks:
+        nets = [NN(layers_pinn, *mine[k], xcos_x2cos2).to(device) for k in range(a, b)]
+        mus = [tuple(mine[k]) for k in range(a, b)]
+        # loss before the step of epochs 1, 1001, 2001, ... == loss after 0, 1000, 2000, ... steps
+        res = pinn.train_fused_batch(nets, "kg", mus, xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u,
+                                     epochs_pinn, lr_pinn, xcos=xcos_x2cos2, trace_every=1000)
+        fin = pinn.train_fused_batch(nets, "kg", mus, xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u,
+                                     1, 0.0, xcos=xcos_x2cos2)           # lr = 0: evaluates the loss, leaves the weights
+        for net, r, f in zip(nets, res, fin):
+            recs.append(dict(net=net, trace=r["trace"][:101].clone(), final=f["loss"].clone()))
+    pinn.train_memo_put(key, tensors, recs)
+    return recs
+
+
 def pinn_test(kg_test, layers_pinn, xcos_x2cos2, xt_resid, IC_xt, IC_u1, IC_u2,
               BC_xt, BC_u, f_hat, epochs_pinn, lr_pinn, xt_test):
     """One full PINN per test parameter (KG_test.py:81-111); the parameters are independent, so several are trained
@@ -64,15 +89,11 @@ def pinn_test(kg_test, layers_pinn, xcos_x2cos2, xt_resid, IC_xt, IC_u1, IC_u2,
     kg_test = np.asarray(kg_test, dtype=np.float64).reshape(-1, 3)
     t0 = time.time()
     lo, hi = offline.shard_bounds(len(kg_test))
-    mine = kg_test[lo:hi]
+    recs = _trained(kg_test[lo:hi], layers_pinn, xcos_x2cos2, xt_resid, IC_xt, IC_u1, IC_u2, BC_xt, BC_u, f_hat, epochs_pinn, lr_pinn)
     local = torch.zeros((hi - lo, xt_test.shape[0]), dtype=torch.float32, device=xt_test.device)
-    for a, b in _chunks(len(mine)):
-        nets = [NN(layers_pinn, *mine[k], xcos_x2cos2).to(device) for k in range(a, b)]
-        pinn.train_fused_batch(nets, "kg", [tuple(mine[k]) for k in range(a, b)], xt_resid, f_hat, IC_xt, IC_u1, IC_u2,
-                               BC_xt, BC_u, epochs_pinn, lr_pinn, xcos=xcos_x2cos2)
-        with torch.no_grad():
-            for k, net in zip(range(a, b), nets):
-                local[k] = net(xt_test)[:, 0]
+    with torch.no_grad():
+        for k, rec in enumerate(recs):
+            local[k] = rec["net"](xt_test)[:, 0]
     soln = offline.gather_rows(local, len(kg_test))
     pinn_soln = soln.t().cpu().numpy().astype(np.float64)
     times = offline.spread_hours(time.time() - t0, len(kg_test))
@@ -84,18 +105,10 @@ def pinn_test_loss(kg_test, layers_pinn, xcos_x2cos2, xt_resid, IC_xt, IC_u1,
     """Loss after 0, 1000, 2000, ... steps and after the last step (KG_test.py:116-140), sharded like pinn_test."""
     kg_test = np.asarray(kg_test, dtype=np.float64).reshape(-1, 3)
     lo, hi = offline.shard_bounds(len(kg_test))
-    mine = kg_test[lo:hi]
+    recs = _trained(kg_test[lo:hi], layers_pinn, xcos_x2cos2, xt_resid, IC_xt, IC_u1, IC_u2, BC_xt, BC_u, f_hat, epochs_pinn, lr_pinn)
     local = torch.zeros((hi - lo, 101), dtype=torch.float32, device=xt_resid.device)
-    for a, b in _chunks(len(mine)):
-        nets = [NN(layers_pinn, *mine[k], xcos_x2cos2).to(device) for k in range(a, b)]
-        mus = [tuple(mine[k]) for k in range(a, b)]
-        # loss before the step of epochs 1, 1001, 2001, ... == loss after 0, 1000, 2000, ... steps
-        res = pinn.train_fused_batch(nets, "kg", mus, xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u,
-                                     epochs_pinn, lr_pinn, xcos=xcos_x2cos2, trace_every=1000)
-        fin = pinn.train_fused_batch(nets, "kg", mus, xt_resid, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u,
-                                     1, 0.0, xcos=xcos_x2cos2)           # lr = 0: evaluates the loss, leaves the weights
-        for k, r, f in zip(range(a, b), res, fin):
-            tr = r["trace"]
-            local[k, :min(101, tr.numel())] = tr[:101]
-            local[k, min(100, int(epochs_pinn / 1000))] = f["loss"]
+    for k, rec in enumerate(recs):
+        tr = rec["trace"]
+        local[k, :min(101, tr.numel())] = tr[:101]
+        local[k, min(100, int(epochs_pinn / 1000))] = rec["final"]
     return offline.gather_rows(local, len(kg_test)).t().cpu().numpy().astype(np.float64)

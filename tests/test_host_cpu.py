@@ -458,3 +458,41 @@ def test_reference_copy_is_byte_identical():
     assert n >= 25
     tracked = subprocess.run(["git", "-C", ROOT, "ls-files", "oracle/_ref"], capture_output=True, text=True).stdout.strip()
     assert tracked == "", "reference sources must not enter the history"
+
+
+def test_training_memo_key_follows_identity_version_and_arguments():
+    """gptpinn.pinn memo of finished test-set trainings: a hit needs the same parameters, epochs, lr, tol, batching and the
+    same data tensors (object identity AND in-place version); a freed tensor invalidates the entry."""
+    import torch
+    from gptpinn import pinn
+    a, b = torch.zeros(5, 2), torch.ones(7)
+    mus = np.array([[1.0, 2.0, 3.0], [4.0, 5.0, 6.0]])
+    key = lambda **kw: pinn.train_memo_key(kw.get("pde", "kg"), kw.get("layers", [2, 40, 40, 1]), kw.get("mus", mus), kw.get("epochs", 100),
+                                           kw.get("lr", 5e-4), kw.get("tol"), kw.get("chunks", [(0, 2)]), kw.get("tensors", (a, b, None)))
+    pinn.train_memo_clear()
+    k0 = key()
+    assert key() == k0 and hash(k0) is not None
+    for other in (key(pde="burgers"), key(layers=[2, 20, 1]), key(mus=mus + 1e-12), key(epochs=101), key(lr=1e-3), key(tol=1e-4),
+                  key(chunks=[(0, 1), (1, 2)]), key(tensors=(a.clone(), b, None)), key(tensors=(a, b, b))):
+        assert other != k0
+    pinn.train_memo_put(k0, (a, b, None), ["rec"])
+    assert pinn.train_memo_get(k0) == ["rec"]
+    a.add_(1.0)                                           # in-place write moves the version counter
+    assert key() != k0 and pinn.train_memo_get(key()) is None
+    k1 = key()
+    pinn.train_memo_put(k1, (a, b, None), ["rec1"])
+    assert pinn.train_memo_get(k1) == ["rec1"]
+    os.environ["GPTPINN_NO_TRAIN_MEMO"] = "1"
+    try:
+        assert pinn.train_memo_get(k1) is None
+    finally:
+        del os.environ["GPTPINN_NO_TRAIN_MEMO"]
+    del b                                                 # the caller's tensor goes away: the entry can never be hit again
+    import gc
+    gc.collect()
+    b = torch.ones(7)
+    assert pinn.train_memo_get(key()) is None
+    for i in range(10):
+        pinn.train_memo_put(("k", i), (a,), [i])
+    assert len(pinn._train_memo) <= pinn.TRAIN_MEMO_ENTRIES
+    pinn.train_memo_clear()

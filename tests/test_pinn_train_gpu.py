@@ -186,6 +186,60 @@ def test_dropin_pinn_test_sweeps_shapes_and_first_records():
     assert 0.75 * want1000 <= got[1, 0] <= 1.25 * want1000
 
 
+def test_pinn_test_and_pinn_test_loss_share_one_training_per_parameter(monkeypatch):
+    """The reference's pinn_test and pinn_test_loss train the same networks twice (NN.__init__ reseeds torch).  The drop-in
+    trains them once: the second call launches nothing and returns exactly what a re-run computes (checked with the memo
+    switched off); an in-place change of any data tensor, other epochs or another order of the calls is a miss / still equal."""
+    import B_data
+    import B_test
+    import KG_test
+    from gptpinn import pinn
+    make, params, t, xcos = _kg_setup(nc=9, ic=16, bc=16, seed=5)
+    xt, f_hat, IC_xt, IC_u1, IC_u2, BC_xt, BC_u = t
+    kg_test = np.array([[-1.2, 0.3, 0.6], [-1.7, 0.9, 0.1], [-1.1, 0.2, 0.9]])
+    layers = np.array([2, 40, 40, 1])
+    xt_test = xt[:40].contiguous()
+    calls = []
+    orig = pinn.train_fused_batch
+    monkeypatch.setattr(pinn, "train_fused_batch", lambda *a, **k: (calls.append(1), orig(*a, **k))[1])
+    args = (kg_test, layers, xcos, xt, IC_xt, IC_u1, IC_u2, BC_xt, BC_u, f_hat, 2300, 5e-4)
+    pinn.train_memo_clear()
+    _, soln = KG_test.pinn_test(*args, xt_test)
+    n1 = len(calls)
+    losses = KG_test.pinn_test_loss(*args)
+    assert n1 == 2 and len(calls) == n1                                   # one chunk: training + final-loss launch; then nothing
+    assert (losses[:3] > 0).all() and (losses[3:] == 0).all()
+    monkeypatch.setenv("GPTPINN_NO_TRAIN_MEMO", "1")
+    losses2 = KG_test.pinn_test_loss(*args)
+    _, soln2 = KG_test.pinn_test(*args, xt_test)
+    assert len(calls) == n1 + 4 and np.array_equal(losses, losses2) and np.array_equal(soln, soln2)
+    monkeypatch.delenv("GPTPINN_NO_TRAIN_MEMO")
+    pinn.train_memo_clear()
+    losses3 = KG_test.pinn_test_loss(*args)                               # the other order: losses first
+    n3 = len(calls)
+    _, soln3 = KG_test.pinn_test(*args, xt_test)
+    assert len(calls) == n3 and np.array_equal(losses, losses3) and np.array_equal(soln, soln3)
+    f_hat.add_(0.0)                                                       # in-place write: version counter moves -> miss
+    KG_test.pinn_test_loss(*args)
+    assert len(calls) == n3 + 2
+    KG_test.pinn_test_loss(*args[:-2], 1200, 5e-4)                        # other epochs -> miss
+    assert len(calls) == n3 + 4
+    # Burgers (tolerance-stopped)
+    xtb, fb, _ = B_data.residual_data(-1.0, 1.0, 0.0, 1.0, 11, 4)
+    ICx, ICu, BCx, BCu = B_data.ICBC_data(-1.0, 1.0, 0.0, 1.0, 12, 12)
+    xtb, fb, ICx, ICu, BCx, BCu = (a.cuda() for a in (xtb, fb, ICx, ICu, BCx, BCu))
+    bl = np.array([2, 20, 20, 20, 20, 1])
+    bargs = (np.array([0.3, 0.05]), bl, xtb, ICx, ICu, BCx, BCu, fb, 1500, 2e-3)
+    pinn.train_memo_clear()
+    n4 = len(calls)
+    _, bs = B_test.pinn_test(*bargs, xtb[:20].contiguous(), 1e-9)
+    bloss = B_test.pinn_test_loss(*bargs, 1e-9)
+    assert len(calls) == n4 + 1
+    monkeypatch.setenv("GPTPINN_NO_TRAIN_MEMO", "1")
+    assert np.array_equal(bloss, B_test.pinn_test_loss(*bargs, 1e-9))
+    assert np.array_equal(bs, B_test.pinn_test(*bargs, xtb[:20].contiguous(), 1e-9)[1])
+
+
 def test_batched_trainings_match_single_trainings():
     """gptpinn_pinn_train_batch: several trainings in one launch = the same trainings one by one (the grid is cut into
     equal CTA groups, so only the order of the gradient partial sums differs: 1e-4 on a 25-step trajectory); each training
