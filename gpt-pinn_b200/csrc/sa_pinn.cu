@@ -11,7 +11,8 @@
 //   zbar_u  = s1 abar_u + s2 (z_x abar_x + z_t abar_t + z_xx abar_xx) + s3 z_x^2 abar_xx
 // All points (collocation, initial, lower / upper boundary) run as ONE batch of N points; tensors are [4][N][W]
 // (channel-major, W = hidden width), so every hidden->hidden map of all four channels is one [4N x W] x [W x W] GEMM
-// -- a plain library GEMM (cuBLAS through torch.mm on the host side, gptpinn/sa_pinn.py); everything else is here.
+// -- a plain library GEMM (cuBLAS through torch.mm on the host side, gptpinn/sa_pinn.py) for the maps and their adjoints;
+// everything else, including the weight-gradient contraction over the 4N rows and the L-BFGS direction, is here.
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math.h>

@@ -10,12 +10,13 @@ L-BFGS of eager_lbfgs.py:14-200.  What is reproduced, statement by statement:
               (AC_main.py:282-298), then up to `newton_iter` L-BFGS iterations (step 0.8, history 50, no line search) on
               the weights only.
 How it runs on the B200: all points go through the network as one batch with four channels (u, u_x, u_t, u_xx) in
-[4][N][W] tensors; activation maps, their hand-derived adjoints, the loss / seed computation and the Adam updates are the
-CUDA kernels of csrc/sa_pinn.cu (C ABI gptpinn_sa_*); the hidden->hidden maps and the weight-gradient contractions are
-plain fp32 library GEMMs ([4N x W] x [W x W], torch.mm -> cuBLAS).  One whole Adam iteration (forward, reverse, three
-optimizer steps) is captured once into a CUDA graph and replayed: no Python, no allocation, no host sync per step; the
-iteration counter of the bias correction lives on the device.  L-BFGS keeps its history on the device and synchronises
-once per iteration for the reference's scalar tests.  No TensorFlow, no autograd, no CPU path.
+[4][N][W] tensors; activation maps, their hand-derived adjoints, the loss / seed computation, the weight- and bias-gradient
+contractions over the 4N rows, the Adam updates and the L-BFGS two-loop recursion are the CUDA kernels of csrc/sa_pinn.cu
+(C ABI gptpinn_sa_*); the hidden->hidden maps and their adjoints are plain fp32 library GEMMs ([4N x W] x [W x W],
+torch.mm -> cuBLAS).  One whole Adam iteration (forward, reverse, three optimizer steps) is captured once into a CUDA graph
+and replayed: no Python, no allocation, no host sync per step; the iteration counter of the bias correction lives on the
+device.  L-BFGS keeps its history on the device (a ring of (s, y) pairs), gets its direction from one kernel launch and
+synchronises once per iteration for the reference's scalar tests.  No TensorFlow, no autograd, no CPU path.
 Parity: TensorFlow is not in this image, so trajectories are statistical only; the loss and every gradient are held to an
 fp64 autograd restatement of the same loss in the test suite (tests/test_sa_pinn.py).
 """
