@@ -10,9 +10,9 @@
 //   zbar_xx = s1 abar_xx,  zbar_t = s1 abar_t,  zbar_x = s1 abar_x + 2 s2 z_x abar_xx,
 //   zbar_u  = s1 abar_u + s2 (z_x abar_x + z_t abar_t + z_xx abar_xx) + s3 z_x^2 abar_xx
 // All points (collocation, initial, lower / upper boundary) run as ONE batch of N points; tensors are [4][N][W]
-// (channel-major, W = hidden width), so every hidden->hidden map of all four channels is one [4N x W] x [W x W] GEMM
-// -- a plain library GEMM (cuBLAS through torch.mm on the host side, gptpinn/sa_pinn.py) for the maps and their adjoints;
-// everything else, including the weight-gradient contraction over the 4N rows and the L-BFGS direction, is here.
+// (channel-major, W = hidden width), so every hidden->hidden map of all four channels is one [4N x W] x [W x W] product:
+// sa_map_kernel (W = 128, activation or its adjoint fused into the epilogue), sa_wgrad_kernel (weight gradients over the 4N
+// rows); other widths compose a library GEMM (torch.mm on the host side, gptpinn/sa_pinn.py) with the elementwise kernels.
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -544,6 +544,140 @@ __global__ void __launch_bounds__(256) sa_colsums_final_kernel(const float *__re
     }
 }
 
+
+// ---- hidden->hidden map of all four channels with the activation in its epilogue (W = 128) -----------------------------------------
+// MODE 0 (forward, AC_main.py:209-213):  Z' = A Wn^T (+ bias on channel 0),  A' = channels of tanh(Z')      -> Z_out, A_out
+// MODE 1 (adjoint):                      Abar = G Wn,  Zbar = act_backward(Z_prev, Abar)                        -> G_out
+// X is [4][N][128] (channel-major rows).  A CTA takes 32 points x 4 channels = 128 rows and ONE half (64) of the output columns --
+// 2 * ceil(N / 32) CTAs of 68 KB shared memory, three per SM: 1296 CTAs on 444 slots for the reference's 20 712 points (2.92 waves;
+// whole 128 x 128 tiles would quantise 648 tiles on 296 slots to three waves of 2.19).  Tile row = 4 * point + channel, so thread
+// (ty, tx) of 16 x 16 -- rows {4 ty .. 4 ty + 3} u {64 + 4 ty ..}, columns 4 tx .. 4 tx + 3 -- ends up with all four channels of two
+// points for its columns: the activation (forward) or its adjoint (reverse) is applied in registers and the pre-activations /
+// activations / adjoints go to global memory once, instead of a GEMM output pass plus an elementwise pass over 42 MB tensors.
+// The K = 128 contraction streams X in four 32-column chunks (cp.async double buffer, rows padded to 36 floats: conflict-free
+// LDS.128 along k); the weight half stays in shared memory as B[k][n] (transposed on the way in for the forward map).
+constexpr int MP_THREADS = 256, MP_PTS = 32, MP_ROWS = 4 * MP_PTS, MP_COLS = 64, MP_K = 128, MP_KC = 32, MP_XS = MP_KC + 4;
+constexpr size_t MP_SMEM = (size_t)(MP_K * MP_COLS + 2 * MP_ROWS * MP_XS) * sizeof(float);
+
+template <int MODE>
+__global__ void __launch_bounds__(MP_THREADS, 3)
+sa_map_kernel(const float *__restrict__ X, const float *__restrict__ Wn, const float *__restrict__ bias, const float *__restrict__ Zp,
+              long long N, float *__restrict__ out0, float *__restrict__ out1)
+{
+    extern __shared__ __align__(16) float mp_sm[];
+    float *Bs = mp_sm;                                       // [MP_K][MP_COLS]
+    float *Xs = mp_sm + MP_K * MP_COLS;                      // [2][MP_ROWS][MP_XS]
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int half = blockIdx.x & 1;
+    const long long p0 = (long long)(blockIdx.x >> 1) * MP_PTS;
+
+    auto load_chunk = [&](int kc, int buf) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const int e = tid + h * MP_THREADS, rho = e >> 3, q = e & 7;          // tile row, float4 within the chunk
+            const long long p = p0 + (rho >> 2);
+            float *dst = Xs + ((size_t)buf * MP_ROWS + rho) * MP_XS + 4 * q;
+            if (p < N) cp_async16(dst, X + ((long long)(rho & 3) * N + p) * MP_K + kc * MP_KC + 4 * q);
+            else *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        cp_async_commit();
+    };
+    load_chunk(0, 0);
+    if (MODE == 0) {                                         // B[k][n] = Wn[64 half + n][k]
+        for (int e = tid; e < MP_COLS * (MP_K / 4); e += MP_THREADS) {
+            const int n = e & (MP_COLS - 1), k4 = e / MP_COLS;
+            const float4 w = *reinterpret_cast<const float4 *>(Wn + (size_t)(half * MP_COLS + n) * MP_K + 4 * k4);
+            Bs[(4 * k4 + 0) * MP_COLS + n] = w.x; Bs[(4 * k4 + 1) * MP_COLS + n] = w.y;
+            Bs[(4 * k4 + 2) * MP_COLS + n] = w.z; Bs[(4 * k4 + 3) * MP_COLS + n] = w.w;
+        }
+    } else {                                                 // B[k][n] = Wn[k][64 half + n]
+        for (int e = tid; e < MP_K * (MP_COLS / 4); e += MP_THREADS) {
+            const int k = e / (MP_COLS / 4), n4 = e % (MP_COLS / 4);
+            *reinterpret_cast<float4 *>(Bs + k * MP_COLS + 4 * n4) = *reinterpret_cast<const float4 *>(Wn + (size_t)k * MP_K + half * MP_COLS + 4 * n4);
+        }
+    }
+    float acc[8][4];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) { acc[a][0] = 0.f; acc[a][1] = 0.f; acc[a][2] = 0.f; acc[a][3] = 0.f; }
+
+    for (int kc = 0; kc < MP_K / MP_KC; ++kc) {
+        const int buf = kc & 1;
+        if (kc + 1 < MP_K / MP_KC) { load_chunk(kc + 1, buf ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();                                     // chunk kc (and, the first time, B) visible to every thread
+        const float *xs = Xs + (size_t)buf * MP_ROWS * MP_XS;
+        const float *bs = Bs + (size_t)kc * MP_KC * MP_COLS + 4 * tx;
+#pragma unroll 2
+        for (int k4 = 0; k4 < MP_KC / 4; ++k4) {
+            float4 xa[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+                xa[a] = *reinterpret_cast<const float4 *>(xs + (a < 4 ? 4 * ty + a : 64 + 4 * ty + (a - 4)) * MP_XS + 4 * k4);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float4 b = *reinterpret_cast<const float4 *>(bs + (4 * k4 + t) * MP_COLS);
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    const float xv = t == 0 ? xa[a].x : (t == 1 ? xa[a].y : (t == 2 ? xa[a].z : xa[a].w));
+                    acc[a][0] = fmaf(xv, b.x, acc[a][0]); acc[a][1] = fmaf(xv, b.y, acc[a][1]);
+                    acc[a][2] = fmaf(xv, b.z, acc[a][2]); acc[a][3] = fmaf(xv, b.w, acc[a][3]);
+                }
+            }
+        }
+        __syncthreads();                                     // the buffer just read is refilled two chunks later
+    }
+
+    // epilogue: rows a = 0..3 are the channels (u, x, t, xx) of point ty, rows 4..7 those of point 16 + ty
+    const int c0 = half * MP_COLS + 4 * tx;
+    const size_t plane = (size_t)N * MP_K;
+#pragma unroll
+    for (int hp = 0; hp < 2; ++hp) {
+        const long long p = p0 + (hp ? 16 + ty : ty);
+        if (p >= N) continue;
+        const size_t o = (size_t)p * MP_K + c0;
+        float r0[4], r1[4], r2[4], r3[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { r0[j] = acc[4 * hp][j]; r1[j] = acc[4 * hp + 1][j]; r2[j] = acc[4 * hp + 2][j]; r3[j] = acc[4 * hp + 3][j]; }
+        if (MODE == 0) {
+            const float4 bv = *reinterpret_cast<const float4 *>(bias + c0);
+            const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+            float a0[4], a1[4], a2[4], a3[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                r0[j] += bb[j];                              // the stored pre-activation carries the bias (the reverse pass reads it)
+                const float s0 = tanhf(r0[j]), s1 = 1.f - s0 * s0, s2 = -2.f * s0 * s1;
+                a0[j] = s0; a1[j] = s1 * r1[j]; a2[j] = s1 * r2[j]; a3[j] = fmaf(s2 * r1[j], r1[j], s1 * r3[j]);
+            }
+            *reinterpret_cast<float4 *>(out0 + o) = make_float4(r0[0], r0[1], r0[2], r0[3]);
+            *reinterpret_cast<float4 *>(out0 + plane + o) = make_float4(r1[0], r1[1], r1[2], r1[3]);
+            *reinterpret_cast<float4 *>(out0 + 2 * plane + o) = make_float4(r2[0], r2[1], r2[2], r2[3]);
+            *reinterpret_cast<float4 *>(out0 + 3 * plane + o) = make_float4(r3[0], r3[1], r3[2], r3[3]);
+            *reinterpret_cast<float4 *>(out1 + o) = make_float4(a0[0], a0[1], a0[2], a0[3]);
+            *reinterpret_cast<float4 *>(out1 + plane + o) = make_float4(a1[0], a1[1], a1[2], a1[3]);
+            *reinterpret_cast<float4 *>(out1 + 2 * plane + o) = make_float4(a2[0], a2[1], a2[2], a2[3]);
+            *reinterpret_cast<float4 *>(out1 + 3 * plane + o) = make_float4(a3[0], a3[1], a3[2], a3[3]);
+        } else {
+            const float4 z0v = *reinterpret_cast<const float4 *>(Zp + o), zxv = *reinterpret_cast<const float4 *>(Zp + plane + o);
+            const float4 ztv = *reinterpret_cast<const float4 *>(Zp + 2 * plane + o), zxxv = *reinterpret_cast<const float4 *>(Zp + 3 * plane + o);
+            const float z0[4] = {z0v.x, z0v.y, z0v.z, z0v.w}, zx[4] = {zxv.x, zxv.y, zxv.z, zxv.w};
+            const float zt[4] = {ztv.x, ztv.y, ztv.z, ztv.w}, zxx[4] = {zxxv.x, zxxv.y, zxxv.z, zxxv.w};
+            float g0[4], g1[4], g2[4], g3[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                    // the arithmetic of sa_act_backward_kernel
+                const float s0 = tanhf(z0[j]), s1 = 1.f - s0 * s0, s2 = -2.f * s0 * s1, s3 = s1 * (6.f * s0 * s0 - 2.f);
+                g3[j] = s1 * r3[j];
+                g2[j] = s1 * r2[j];
+                g1[j] = fmaf(s1, r1[j], 2.f * s2 * zx[j] * r3[j]);
+                g0[j] = s1 * r0[j] + s2 * (zx[j] * r1[j] + zt[j] * r2[j] + zxx[j] * r3[j]) + s3 * zx[j] * zx[j] * r3[j];
+            }
+            *reinterpret_cast<float4 *>(out0 + o) = make_float4(g0[0], g0[1], g0[2], g0[3]);
+            *reinterpret_cast<float4 *>(out0 + plane + o) = make_float4(g1[0], g1[1], g1[2], g1[3]);
+            *reinterpret_cast<float4 *>(out0 + 2 * plane + o) = make_float4(g2[0], g2[1], g2[2], g2[3]);
+            *reinterpret_cast<float4 *>(out0 + 3 * plane + o) = make_float4(g3[0], g3[1], g3[2], g3[3]);
+        }
+    }
+}
+
 }  // namespace gp
 
 using namespace gp;
@@ -702,4 +836,43 @@ extern "C" int gptpinn_sa_layer0_grad(const float *G_dev, const float *xt_dev, l
     gp::sa_colsums_final_kernel<true><<<(W + 7) / 8, 256, 0, (cudaStream_t)stream>>>(workspace_dev, grid, W, gb0_dev, gW0_dev);
     SA_LAUNCHED();
     return GPTPINN_OK;
+}
+
+static int sa_map_launch(int mode, const float *X, const float *Wn, const float *bias, const float *Zp, long long N, int W, float *out0, float *out1,
+                         cudaStream_t st)
+{
+    if (W != gp::MP_K) return GPTPINN_E_INVALID;             // (other widths: the caller composes a library GEMM with the elementwise kernels)
+    const uintptr_t al = reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Wn) | reinterpret_cast<uintptr_t>(out0) |
+                         reinterpret_cast<uintptr_t>(mode == 0 ? (const void *)out1 : (const void *)Zp) |
+                         reinterpret_cast<uintptr_t>(mode == 0 ? (const void *)bias : (const void *)X);
+    if (al & 15u) return GPTPINN_E_INVALID;
+    const long long tiles = (N + gp::MP_PTS - 1) / gp::MP_PTS;
+    if (tiles > (1LL << 29)) return GPTPINN_E_INVALID;
+    auto kern = mode == 0 ? gp::sa_map_kernel<0> : gp::sa_map_kernel<1>;
+    // the shared-memory opt-in is set once per device and kernel: this entry point also runs under stream capture (the Adam
+    // iteration is a CUDA graph), where only the launch itself should be issued
+    static int attr_dev[2] = {-1, -1};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return GPTPINN_E_CUDA;
+    if (attr_dev[mode] != dev) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gp::MP_SMEM) != cudaSuccess) return GPTPINN_E_CUDA;
+        attr_dev[mode] = dev;
+    }
+    kern<<<(unsigned)(2 * tiles), gp::MP_THREADS, gp::MP_SMEM, st>>>(X, Wn, bias, Zp, N, out0, out1);
+    SA_LAUNCHED();
+    return GPTPINN_OK;
+}
+
+extern "C" int gptpinn_sa_map_forward(const float *A_dev, const float *W_dev, const float *bias_dev, long long N, int W, float *Z_out_dev,
+                                      float *A_out_dev, void *stream)
+{
+    SA_CHECK(A_dev && W_dev && bias_dev && Z_out_dev && A_out_dev && N > 0, "gptpinn_sa_map_forward");
+    return sa_map_launch(0, A_dev, W_dev, bias_dev, nullptr, N, W, Z_out_dev, A_out_dev, (cudaStream_t)stream);
+}
+
+extern "C" int gptpinn_sa_map_adjoint(const float *G_dev, const float *W_dev, const float *Zprev_dev, long long N, int W, float *G_out_dev,
+                                      void *stream)
+{
+    SA_CHECK(G_dev && W_dev && Zprev_dev && G_out_dev && N > 0 && G_out_dev != G_dev, "gptpinn_sa_map_adjoint");
+    return sa_map_launch(1, G_dev, W_dev, nullptr, Zprev_dev, N, W, G_out_dev, nullptr, (cudaStream_t)stream);
 }

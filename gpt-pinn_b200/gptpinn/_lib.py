@@ -80,7 +80,7 @@ EXPORTS = ("gptpinn_version", "gptpinn_last_error", "gptpinn_create", "gptpinn_d
            "gptpinn_sa_layer0", "gptpinn_sa_act_forward", "gptpinn_sa_act_backward", "gptpinn_sa_output_forward",
            "gptpinn_sa_loss_workspace_floats", "gptpinn_sa_loss", "gptpinn_sa_output_backward", "gptpinn_sa_tick", "gptpinn_sa_adam",
            "gptpinn_sa_lbfgs_max_params", "gptpinn_sa_lbfgs_direction", "gptpinn_sa_workspace_floats", "gptpinn_sa_wgrad",
-           "gptpinn_sa_bias_grad", "gptpinn_sa_layer0_grad")
+           "gptpinn_sa_bias_grad", "gptpinn_sa_layer0_grad", "gptpinn_sa_map_forward", "gptpinn_sa_map_adjoint")
 
 _lib = None
 

@@ -10,10 +10,10 @@ L-BFGS of eager_lbfgs.py:14-200.  What is reproduced, statement by statement:
               (AC_main.py:282-298), then up to `newton_iter` L-BFGS iterations (step 0.8, history 50, no line search) on
               the weights only.
 How it runs on the B200: all points go through the network as one batch with four channels (u, u_x, u_t, u_xx) in
-[4][N][W] tensors; activation maps, their hand-derived adjoints, the loss / seed computation, the weight- and bias-gradient
-contractions over the 4N rows, the Adam updates and the L-BFGS two-loop recursion are the CUDA kernels of csrc/sa_pinn.cu
-(C ABI gptpinn_sa_*); the hidden->hidden maps and their adjoints are plain fp32 library GEMMs ([4N x W] x [W x W],
-torch.mm -> cuBLAS).  One whole Adam iteration (forward, reverse, three optimizer steps) is captured once into a CUDA graph
+[4][N][W] tensors; the hidden->hidden maps with the activation in their epilogue (forward and adjoint), the weight- and
+bias-gradient contractions over the 4N rows, the loss / seed computation, the Adam updates and the L-BFGS two-loop recursion
+are the CUDA kernels of csrc/sa_pinn.cu (C ABI gptpinn_sa_*).  torch.mm is left for the 1 x 4N output-layer gradient and,
+composed with the elementwise activation kernels, for hidden widths other than the reference's 128.  One whole Adam iteration (forward, reverse, three optimizer steps) is captured once into a CUDA graph
 and replayed: no Python, no allocation, no host sync per step; the iteration counter of the bias correction lives on the
 device.  L-BFGS keeps its history on the device (a ring of (s, y) pairs), gets its direction from one kernel launch and
 synchronises once per iteration for the reference's scalar tests.  No TensorFlow, no autograd, no CPU path.
@@ -22,6 +22,7 @@ fp64 autograd restatement of the same loss in the test suite (tests/test_sa_pinn
 """
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -73,6 +74,26 @@ class CudaOps:
 
     def tick(self, step):
         _lib.check(self.L.gptpinn_sa_tick(self._p(step), self._s()), "gptpinn_sa_tick")
+
+    def map_forward(self, A, Wn, bias, Z_out, A_out):
+        """Z_out = A Wn^T (+ bias on channel 0), A_out = channels of tanh(Z_out): one kernel for W = 128 (the reference's width)"""
+        W = A.shape[2]
+        if W == 128 and not os.environ.get("GPTPINN_SA_NO_FUSED_MAPS"):
+            _lib.check(self.L.gptpinn_sa_map_forward(self._p(A), self._p(Wn), self._p(bias), C.c_longlong(A.shape[1]), C.c_int(W), self._p(Z_out),
+                                                     self._p(A_out), self._s()), "gptpinn_sa_map_forward")
+        else:                                         # other widths: library GEMM + the elementwise kernel
+            torch.mm(A.view(-1, W), Wn.t(), out=Z_out.view(-1, W))
+            self.act_forward(Z_out, bias, A_out)
+
+    def map_adjoint(self, G, Wn, Zprev, G_out):
+        """G_out = adjoint of the previous layer's pre-activations = act_backward(Zprev, G Wn)"""
+        W = G.shape[2]
+        if W == 128 and not os.environ.get("GPTPINN_SA_NO_FUSED_MAPS"):
+            _lib.check(self.L.gptpinn_sa_map_adjoint(self._p(G), self._p(Wn), self._p(Zprev), C.c_longlong(G.shape[1]), C.c_int(W), self._p(G_out),
+                                                     self._s()), "gptpinn_sa_map_adjoint")
+        else:
+            torch.mm(G.view(-1, W), Wn, out=G_out.view(-1, W))
+            self.act_backward(Zprev, G_out)
 
     def wgrad(self, G, A, out):
         """out[j][i] = sum over channels and points of G[c][r][j] A[c][r][i]: the weight gradient of a hidden->hidden map"""
@@ -180,10 +201,9 @@ class SAPinn:
         """Fills self.loss4 = (total, mse_u, mse_b, mse_f), self.grad (flat, d total / d weights), self.gwf, self.gwu."""
         o, N, W, NH = self.ops, self.N, self.W, self.NH
         o.layer0(self.xt, self.Wv[0], self.bv[0], self.Z[0])
-        for l in range(NH):
-            o.act_forward(self.Z[l], None if l == 0 else self.bv[l], self.A[l])
-            if l < NH - 1:
-                torch.mm(self.A[l].view(4 * N, W), self.Wv[l + 1].t(), out=self.Z[l + 1].view(4 * N, W))
+        o.act_forward(self.Z[0], None, self.A[0])
+        for l in range(NH - 1):
+            o.map_forward(self.A[l], self.Wv[l + 1], self.bv[l + 1], self.Z[l + 1], self.A[l + 1])
         o.output_forward(self.A[NH - 1], self.Wv[NH], self.bv[NH], self.U)
         o.loss(self.U, self.NR, self.NI, self.NB, self.u0, self.wf, self.wu, self.lmbda, self.eps, self.Ubar, self.gwf, self.gwu, self.loss4)
         # reverse
@@ -191,12 +211,12 @@ class SAPinn:
         torch.sum(self.Ubar[0], dim=0, keepdim=True, out=self.gb[NH])
         G, G2 = self.G, self.G2
         o.output_backward(self.Ubar, self.Wv[NH], G)
+        o.act_backward(self.Z[NH - 1], G)                 # G: adjoint of the pre-activations of the last hidden layer
         for l in range(NH - 1, -1, -1):
-            o.act_backward(self.Z[l], G)
             if l > 0:
                 o.bias_grad(G, self.gb[l])
                 o.wgrad(G, self.A[l - 1], self.gW[l])
-                torch.mm(G.view(4 * N, W), self.Wv[l], out=G2.view(4 * N, W))
+                o.map_adjoint(G, self.Wv[l], self.Z[l - 1], G2)
                 G, G2 = G2, G
             else:
                 o.layer0_grad(G, self.xt, self.gW[0], self.gb[0])

@@ -290,6 +290,14 @@ int  gptpinn_sa_bias_grad(const float *G_dev, long long N, int W, float *gb_dev,
 int  gptpinn_sa_layer0_grad(const float *G_dev, const float *xt_dev, long long N, int W, float *gW0_dev, float *gb0_dev,
                             float *workspace_dev, void *stream);
 
+/* Hidden->hidden map of all four channels with the activation in its epilogue; tensors are [4][N][W], W_dev is the nn.Linear matrix
+ * [out][in], W must be 128 (GPTPINN_E_INVALID otherwise: compose a GEMM with gptpinn_sa_act_forward / _backward), pointers 16-byte
+ * aligned.  forward: Z_out = A W^T (+ bias on channel 0), A_out = channels of tanh(Z_out).  adjoint: G_out = act_backward(Zprev, G W)
+ * (the adjoint of the previous layer's pre-activations; G_out must not alias G).                                                      */
+int  gptpinn_sa_map_forward(const float *A_dev, const float *W_dev, const float *bias_dev, long long N, int W, float *Z_out_dev,
+                            float *A_out_dev, void *stream);
+int  gptpinn_sa_map_adjoint(const float *G_dev, const float *W_dev, const float *Zprev_dev, long long N, int W, float *G_out_dev, void *stream);
+
 /* L-BFGS search direction d = -H g from the k most recent (s, y) pairs (the two-loop recursion of eager_lbfgs.py:80-106) in one
  * launch.  S_dev / Y_dev are rings of `hist` rows of `ld` floats: pair i (i = 0 oldest ... k-1 newest) sits in row (start + i) % hist,
  * ro_dev[row] = 1 / <y, s> of the pair in that row, Hdiag = <y, s> / <y, y> of the newest pair.  k = 0: d = -Hdiag g.  The vector must

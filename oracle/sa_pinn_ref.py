@@ -115,6 +115,16 @@ class TorchOps:
     def output_backward(self, Ubar, Wout, G):
         G[:] = Ubar[:, :, None] * Wout.reshape(1, 1, -1)
 
+    def map_forward(self, A, Wn, bias, Z_out, A_out):
+        W = A.shape[2]
+        Z_out.reshape(-1, W)[:] = A.reshape(-1, W) @ Wn.t()
+        self.act_forward(Z_out, bias, A_out)
+
+    def map_adjoint(self, G, Wn, Zprev, G_out):
+        W = G.shape[2]
+        G_out.reshape(-1, W)[:] = G.reshape(-1, W) @ Wn
+        self.act_backward(Zprev, G_out)
+
     def wgrad(self, G, A, out):
         W = G.shape[2]
         out[:] = G.reshape(-1, W).t() @ A.reshape(-1, W)

@@ -159,6 +159,22 @@ def test_every_sa_kernel_matches_the_torch_recurrences_gpu():
     cu.output_backward(outs_c[0], Wout.to(dev), Gc2)
     th.output_backward(outs_c[0].cpu().double(), Wout.double(), Gt2)
     assert torch.allclose(Gc2.cpu().double(), Gt2, rtol=1e-6, atol=1e-9)
+    # hidden->hidden maps with the activation in the epilogue (W = 128: one kernel; other widths: library GEMM + elementwise kernel),
+    # forward and adjoint, ragged point counts, against the float64 composition of the same fp32 inputs
+    for Nn, Ww in ((777, 128), (20712, 128), (33, 128), (1, 128), (32, 128), (300, 64)):
+        Ain, Gin, Zp = 0.5 * r(4, Nn, Ww), r(4, Nn, Ww), r(4, Nn, Ww)
+        Wn, bn = r(Ww, Ww) / Ww ** 0.5, 0.1 * r(Ww)
+        Zo, Ao = torch.full((4, Nn, Ww), float("nan"), device=dev), torch.full((4, Nn, Ww), float("nan"), device=dev)
+        cu.map_forward(Ain.to(dev), Wn.to(dev), bn.to(dev), Zo, Ao)
+        Zr, Ar = torch.zeros(4, Nn, Ww, dtype=torch.float64), torch.zeros(4, Nn, Ww, dtype=torch.float64)
+        th.map_forward(Ain.double(), Wn.double(), bn.double(), Zr, Ar)
+        assert torch.allclose(Zo.cpu().double(), Zr, rtol=1e-5, atol=2e-6), (Nn, Ww)
+        assert torch.allclose(Ao.cpu().double(), Ar, rtol=1e-5, atol=5e-6), (Nn, Ww)
+        Go = torch.full((4, Nn, Ww), float("nan"), device=dev)
+        cu.map_adjoint(Gin.to(dev), Wn.to(dev), Zp.to(dev), Go)
+        Gr = torch.zeros(4, Nn, Ww, dtype=torch.float64)
+        th.map_adjoint(Gin.double(), Wn.double(), Zp.double(), Gr)
+        assert torch.allclose(Go.cpu().double(), Gr, rtol=1e-5, atol=2e-5), (Nn, Ww)
     # weight / bias gradient contractions: the register-tile kernel (W = 128, aligned), its zero-padded path (W < 128, ragged
     # row counts, fewer row tiles than CTAs), the library fallback (W > 128), against float64 sums of the same fp32 inputs
     for Nn, Ww in ((777, 128), (5003, 128), (20712, 128), (7, 128), (333, 48), (1, 12), (90, 160)):
