@@ -106,11 +106,19 @@ class CudaOps:
 
     def bias_grad(self, G, gb):
         """gb[j] = sum over the points of G[0][r][j]"""
+        if G.shape[2] > 256:                          # wider than the kernel's column mapping: library reduction
+            torch.sum(G[0], dim=0, out=gb)
+            return
         _lib.check(self.L.gptpinn_sa_bias_grad(self._p(G), C.c_longlong(G.shape[1]), C.c_int(G.shape[2]), self._p(gb), self._p(self.ws2), self._s()),
                    "gptpinn_sa_bias_grad")
 
     def layer0_grad(self, G, xt, gW0, gb0):
         """gradients of the first map from the adjoints of its pre-activations (inputs (x, t), channels (x,1,0,0) / (t,0,1,0))"""
+        if G.shape[2] > 256:
+            torch.sum(G[0], dim=0, out=gb0)
+            gW0[:, 0] = torch.mv(G[0].t(), xt[:, 0]) + torch.sum(G[1], dim=0)
+            gW0[:, 1] = torch.mv(G[0].t(), xt[:, 1]) + torch.sum(G[2], dim=0)
+            return
         _lib.check(self.L.gptpinn_sa_layer0_grad(self._p(G), self._p(xt), C.c_longlong(G.shape[1]), C.c_int(G.shape[2]), self._p(gW0), self._p(gb0),
                                                  self._p(self.ws2), self._s()), "gptpinn_sa_layer0_grad")
 
