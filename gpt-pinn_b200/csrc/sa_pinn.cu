@@ -370,7 +370,7 @@ sa_lbfgs_direction_cluster_kernel(const float *__restrict__ S, const float *__re
 }
 
 
-// ---- weight-gradient contraction  out[j][i] = sum_r G[r][j] A[r][i]  over R = 4N rows (AC_main.py:268-272, the tape's dW) ----------
+// ---- weight-gradient contraction  out[j][i] = sum_r G[r][j] A[r][i]  over R = 4N rows (AC_main.py:254-265, the tape's dW) ----------
 // A [W x R] x [R x W] product with R ~ 8*10^4 and W = 128: the library's split-K kernel ran it at 17 TFLOP/s (a third of the
 // reverse pass).  Here the ROWS are cut into one chunk per CTA (2 CTAs per SM); a CTA streams its chunk through a double-buffered
 // shared-memory stage (cp.async, 16 rows of both matrices per stage) and keeps the whole 128 x 128 product in registers: thread

@@ -278,7 +278,7 @@ int  gptpinn_sa_tick(int *step_dev, void *stream);
 int  gptpinn_sa_adam(float *p_dev, float *m_dev, float *v_dev, const float *g_dev, long long n, const int *step_dev,
                      double lr, double beta1, double beta2, double eps, int ascent, void *stream);
 
-/* Weight-gradient contraction of a hidden->hidden map over all channels and points (the tape's dW of AC_main.py:268-272):
+/* Weight-gradient contraction of a hidden->hidden map over all channels and points (the tape's dW of AC_main.py:254-265):
  * out[j][i] = sum_r G[r][j] A[r][i], G / A row-major [R][W] (R = 4 N rows), out row-major [W][W]; W <= 128.  Row chunks per CTA,
  * partial products in workspace_dev (gptpinn_sa_workspace_floats() floats), summed in a fixed order.                                */
 long long gptpinn_sa_workspace_floats(void);
