@@ -212,7 +212,46 @@ def aux_measurements(device, d, ffma_peak):
     pinn.train_fused_batch(*bargs, 10, 5e-4, xcos=d["xcos"])
     dt, _ = _timed(lambda: pinn.train_fused_batch(*bargs, n_ep // 2, 5e-4, xcos=d["xcos"]))
     out["pinn_train_batch8_us_per_epoch_per_training"] = 1e6 * dt / (n_ep // 2) / 8
+    # ---- SA-PINN trainer (config 3's full-order solver, AC_main.py:204-339) at the reference sizes; single process only
+    try:
+        import torch.distributed as _dist
+        if not (_dist.is_available() and _dist.is_initialized()):
+            out.update(_sa_pinn_timings(device))
+    except Exception as e:                             # a secondary row must never hide the headline
+        out["sa_pinn_error"] = repr(e)
     return out
+
+
+def _sa_pinn_timings(device):
+    """ms per Adam iteration (CUDA graph replay) and per L-BFGS iteration of gptpinn.sa_pinn.SAPinn: [2,128,128,128,128,1],
+    20 000 collocation + 512 initial + 2 x 100 boundary points (AC_main.py:49-51, 125)."""
+    from gptpinn.sa_pinn import SAPinn
+    g = torch.Generator().manual_seed(0)
+    NRs, NIs, NBs = 20000, 512, 100
+    xt_f = torch.stack((2 * torch.rand(NRs, generator=g) - 1, torch.rand(NRs, generator=g)), 1).to(device)
+    x0 = torch.linspace(-1, 1, NIs)
+    xt0 = torch.stack((x0, torch.zeros(NIs)), 1).to(device)
+    u0 = (x0 ** 2 * torch.cos(np.pi * x0)).to(device)
+    tb = torch.rand(NBs, generator=g)
+    xt_lb, xt_ub = torch.stack((-torch.ones(NBs), tb), 1).to(device), torch.stack((torch.ones(NBs), tb), 1).to(device)
+    m = SAPinn([2, 128, 128, 128, 128, 1], xt_f, xt0, u0, xt_lb, xt_ub, 1e-4, 5.0, seed=1)
+    m.adam_fit(20)
+    res = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    m.adam_fit(200)
+    e1.record()
+    torch.cuda.synchronize()
+    res["sa_pinn_adam_ms_per_iter"] = e0.elapsed_time(e1) / 200
+    m.lbfgs_fit(10, 0.8)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    fh = m.lbfgs_fit(100, 0.8)
+    torch.cuda.synchronize()
+    res["sa_pinn_lbfgs_ms_per_iter"] = 1e3 * (time.perf_counter() - t0) / max(len(fh) - 1, 1)
+    res["sa_pinn_loss_after_320_iterations"] = float(fh[-1])
+    return res
 
 
 class ClockSampler:
